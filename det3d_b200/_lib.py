@@ -1,0 +1,131 @@
+"""ctypes binding of the det3d_b200 C ABI (include/det3d_b200.h).
+
+The library is the product: there is no Python/CPU fallback.  If the shared
+object is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdet3d_b200.so")
+
+D3B_OK = 0
+ALGO_SIMT = 0
+ALGO_TC = 1
+BOX_XYXYR = 0
+BOX_XYWLR = 1
+
+
+class D3BError(RuntimeError):
+    pass
+
+
+class VoxelCfg(C.Structure):
+    _fields_ = [
+        ("voxel_size", C.c_float * 3),
+        ("range_min", C.c_float * 3),
+        ("grid", C.c_int32 * 3),
+        ("ndim", C.c_int32),
+        ("max_points", C.c_int32),
+        ("max_voxels", C.c_int32),
+    ]
+
+
+class SiteIndex(C.Structure):
+    _fields_ = [
+        ("spatial", C.c_int32 * 3),
+        ("batch", C.c_int32),
+        ("hash_keys", C.c_void_p),
+        ("hash_vals", C.c_void_p),
+        ("hash_cap", C.c_int32),
+        ("bitmap", C.c_void_p),
+        ("word_prefix", C.c_void_p),
+        ("n_words", C.c_int64),
+    ]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("c_in", C.c_int32),
+        ("c_out", C.c_int32),
+        ("k_vol", C.c_int32),
+        ("weight", C.c_void_p),
+        ("weight_packed", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("relu", C.c_int32),
+        ("algo", C.c_int32),
+    ]
+
+
+_I3 = C.c_int32 * 3
+_vp, _i32, _i64, _sz, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); mirrors include/det3d_b200.h one to one.
+SIGNATURES = {
+    "d3b_last_error": (C.c_char_p, []),
+    "d3b_abi_version": (C.c_int, []),
+    "d3b_launch_count": (C.c_ulonglong, []),
+    "d3b_voxelize_workspace_bytes": (_sz, [C.POINTER(VoxelCfg), _i32, _i32]),
+    "d3b_voxelize": (C.c_int, [C.POINTER(VoxelCfg), _vp, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "d3b_rulebook_workspace_bytes": (_sz, [_i64]),
+    "d3b_index_build_hash": (C.c_int, [_vp, _vp, _i32, C.POINTER(SiteIndex), _vp]),
+    "d3b_rulebook_subm": (C.c_int, [_vp, _vp, _i32, C.POINTER(SiteIndex), _I3, _vp, _vp, _vp]),
+    "d3b_rulebook_conv": (C.c_int, [_vp, _vp, _i32, C.POINTER(SiteIndex), _I3, _I3, _I3, C.POINTER(SiteIndex), _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "d3b_conv_packed_weight_floats": (_sz, [_i32, _i32, _i32]),
+    "d3b_conv_pack_weight": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "d3b_sparse_conv": (C.c_int, [_vp, _vp, _vp, _vp, _i32, C.POINTER(ConvParams), _vp, _vp]),
+    "d3b_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
+    "d3b_boxes_iou_bev": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "d3b_nms_workspace_bytes": (_sz, [_i32]),
+    "d3b_rotate_nms": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "d3b_normal_nms": (C.c_int, [_vp, _i32, _vp, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise D3BError(
+                    "det3d_b200 native library missing at %s -- run `python -m det3d_b200.build` "
+                    "(there is no CPU fallback)" % LIB_PATH
+                )
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def check(status, what=""):
+    if status != D3B_OK:
+        msg = lib().d3b_last_error()
+        raise D3BError("%s failed (status %d): %s" % (what or "det3d_b200 call", status, (msg or b"").decode()))
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().d3b_launch_count())

@@ -1,0 +1,73 @@
+// Shared helpers for the det3d_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "det3d_b200.h"
+
+namespace d3b {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define D3B_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      d3b::set_error(__VA_ARGS__);      \
+      return D3B_ERR_INVALID_ARG;       \
+    }                                   \
+  } while (0)
+
+#define D3B_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      d3b::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                   \
+                     cudaGetErrorString(e__));                                      \
+      return D3B_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define D3B_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    d3b::count_launch();                                                            \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      d3b::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__,               \
+                     cudaGetErrorString(e__));                                      \
+      return D3B_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+// ---- device constants --------------------------------------------------------
+constexpr int kNumSMs = 148;  // B200
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Grid for a grid-stride kernel over `n` items: enough CTAs to cover n but
+// never more than `waves` full waves of the 148 SMs at `ctas_per_sm`.
+static inline int grid_for(long long n, int block, int ctas_per_sm = 8) {
+  long long want = (n + block - 1) / block;
+  long long cap = (long long)kNumSMs * ctas_per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// 64-bit mix (splitmix64 finaliser) for the open-addressing tables.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+
+constexpr unsigned long long kEmptyKey = ~0ULL;  // memset 0xff
+constexpr int kSentinelMin = 0x7f000000;         // memset 0x7f -> 0x7f7f7f7f == "empty"
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+}  // namespace d3b

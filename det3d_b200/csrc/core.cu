@@ -1,0 +1,28 @@
+// Error text, ABI version and the launch counter shared by every entry point.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace d3b {
+
+static thread_local char g_error[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+}  // namespace d3b
+
+extern "C" const char* d3b_last_error(void) { return d3b::g_error; }
+extern "C" int d3b_abi_version(void) { return 1; }
+extern "C" unsigned long long d3b_launch_count(void) {
+  return d3b::g_launches.load(std::memory_order_relaxed);
+}

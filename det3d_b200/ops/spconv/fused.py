@@ -1,0 +1,195 @@
+"""Fused, sync-free executor for a Det3D sparse middle encoder.
+
+Walks the `middle_conv` SparseSequential of SpMiddleFHD / SpMiddleResNetFHD
+(det3d/models/backbones/scn.py:106-157, 323-355), folds every
+`conv -> BatchNorm1d(eval) -> ReLU` triple (and every SparseBasicBlock,
+scn.py:46-89, including its residual add) into one kernel launch per conv, and
+runs rulebooks + convs + `.dense()` back to back on the current stream with
+all row counts kept on the device.  Buffers are sized once per
+(row capacity, batch) and reused, so the sequence is CUDA-graph capturable.
+"""
+import torch
+from torch import nn
+
+from . import core
+from .modules import SparseConvolution
+
+
+class _Layer:
+    __slots__ = ("conv", "bn", "relu", "residual", "save_identity", "cw", "sig")
+
+    def __init__(self, conv, bn, relu, residual=False, save_identity=False):
+        self.conv, self.bn, self.relu = conv, bn, relu
+        self.residual = residual            # add the saved block input before the ReLU
+        self.save_identity = save_identity  # this layer's INPUT is a block input
+        self.cw = None
+        self.sig = None
+
+
+def _bn_fold(bn):
+    """BatchNorm1d(eval) -> per-channel (scale, shift), computed in fp64."""
+    var = bn.running_var.detach().double()
+    mean = bn.running_mean.detach().double()
+    gamma = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(var)
+    beta = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(var)
+    scale = gamma / torch.sqrt(var + bn.eps)
+    shift = beta - mean * scale
+    return scale.float(), shift.float()
+
+
+def _is_basic_block(m):
+    return all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2", "relu")) and isinstance(
+        getattr(m, "conv1"), SparseConvolution
+    )
+
+
+def compile_plan(middle_conv):
+    """middle_conv (SparseSequential) -> list[_Layer]."""
+    mods = list(middle_conv._modules.values())
+    plan = []
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, SparseConvolution):
+            bn = relu = None
+            j = i + 1
+            if j < len(mods) and isinstance(mods[j], nn.modules.batchnorm._BatchNorm):
+                bn = mods[j]
+                j += 1
+            if j < len(mods) and isinstance(mods[j], nn.ReLU):
+                relu = True
+                j += 1
+            plan.append(_Layer(m, bn, bool(relu)))
+            i = j
+        elif _is_basic_block(m):
+            if getattr(m, "downsample", None) is not None:
+                raise NotImplementedError("SparseBasicBlock.downsample is unused by the Det3D configs")
+            plan.append(_Layer(m.conv1, m.bn1, True, save_identity=True))
+            plan.append(_Layer(m.conv2, m.bn2, True, residual=True))
+            i += 1
+        else:
+            raise NotImplementedError("cannot fuse module %r inside a sparse middle encoder" % type(m).__name__)
+    return plan
+
+
+class FusedSparseEncoder:
+    def __init__(self, middle_conv):
+        self.plan = compile_plan(middle_conv)
+        self._state = None
+        self.algo_override = None  # testing hook: force SIMT / TC for every layer
+
+    # ---- parameters ------------------------------------------------------------
+    def _refresh_weights(self, device):
+        for L in self.plan:
+            tensors = [L.conv.weight, L.conv.bias]
+            if L.bn is not None:
+                tensors += [L.bn.weight, L.bn.bias, L.bn.running_mean, L.bn.running_var]
+            sig = tuple((None if t is None else (t._version, t.data_ptr())) for t in tensors) + (self.algo_override,)
+            if L.cw is not None and L.sig == sig:
+                continue
+            if L.bn is not None and L.bn.training:
+                raise RuntimeError("det3d_b200 sparse encoders are inference-only: call .eval() first")
+            scale = shift = None
+            if L.bn is not None:
+                scale, shift = _bn_fold(L.bn)
+                scale, shift = scale.to(device), shift.to(device)
+            L.cw = core.ConvWeights(
+                L.conv.weight.to(device), bias=None if L.conv.bias is None else L.conv.bias.to(device),
+                scale=scale, shift=shift, relu=L.relu, algo=self.algo_override,
+            )
+            L.sig = sig
+
+    # ---- buffers -----------------------------------------------------------------
+    def _build_state(self, cap0, spatial, batch, device):
+        st = {"cap0": cap0, "spatial": tuple(spatial), "batch": batch, "device": device}
+        n0 = torch.zeros(2, dtype=torch.int32, device=device)
+        coors0 = torch.zeros((max(cap0, 1), 4), dtype=torch.int32, device=device)
+        level = core.SparseLevel(coors0, n0, cap0, spatial, batch).build_hash_index()
+        st["level0"] = level
+        steps = []       # (layer, rulebook, build_fn or None)
+        keyed = {}       # (indice_key) -> rulebook
+        pools = {}
+        cur = level
+        for L in self.plan:
+            conv = L.conv
+            build = None
+            if conv.subm:
+                key = (conv.indice_key, id(cur), tuple(conv.kernel_size)) if conv.indice_key is not None else None
+                rb = keyed.get(key) if key is not None else None
+                if rb is None:
+                    rb = core.alloc_subm_rulebook(cur, conv.kernel_size)
+                    build = core.build_subm_rulebook
+                    if key is not None:
+                        keyed[key] = rb
+            else:
+                rb = core.alloc_conv_rulebook(cur, conv.kernel_size, conv.stride, conv.padding)
+                build = core.build_conv_rulebook
+                cur = rb.out_level
+            pools.setdefault((rb.out_level.cap, conv.out_channels), [])
+            steps.append((L, rb, build))
+        st["steps"] = steps
+        st["pools"] = pools
+        st["final_level"] = cur
+        c_last = self.plan[-1].conv.out_channels
+        d, h, w = cur.spatial
+        st["dense"] = torch.empty((batch, c_last, d, h, w), dtype=torch.float32, device=device)
+        return st
+
+    @staticmethod
+    def _take(pools, cap, c, busy, device):
+        pool = pools[(cap, c)]
+        for t in pool:
+            if all(t is not b for b in busy):
+                return t
+        t = torch.empty((max(cap, 1), c), dtype=torch.float32, device=device)
+        pool.append(t)
+        return t
+
+    # ---- run ------------------------------------------------------------------------
+    def run(self, features, coors, batch_size, spatial, n_dev=None, row_cap=None):
+        """features [M, C] f32, coors [M, 4] int (b,z,y,x) -> dense [B, C_out, D, H, W].
+
+        With `n_dev` (int32[>=1] device tensor) only the first n_dev[0] rows are
+        live and M is a capacity; otherwise all M rows are live.
+        """
+        device = features.device
+        m = features.shape[0]
+        cap_needed = m if row_cap is None else max(row_cap, m)
+        st = self._state
+        if (st is None or st["cap0"] < cap_needed or st["batch"] != batch_size
+                or st["spatial"] != tuple(spatial) or st["device"] != device):
+            st = self._state = self._build_state(cap_needed, spatial, batch_size, device)
+        self._refresh_weights(device)
+        lvl0 = st["level0"]
+        # adopt the caller's coordinate rows (zero-copy) for this run
+        coors = coors.to(torch.int32).contiguous()
+        feats = features.to(torch.float32).contiguous()
+        if m > 0:
+            lvl0.coors[:m].copy_(coors)
+        if n_dev is None:
+            lvl0.n.fill_(m)
+        else:
+            lvl0.n[:1].copy_(n_dev.reshape(-1)[:1].to(torch.int32))
+            lvl0.n[1:2].copy_(lvl0.n[:1])
+        lvl0.rebuild_index()
+
+        x = feats
+        identity = None
+        for L, rb, build in st["steps"]:
+            if build is not None:
+                build(rb)
+            if L.save_identity:
+                identity = x
+            out = self._take(st["pools"], rb.out_level.cap, L.conv.out_channels, (x, identity), device)
+            core.sparse_conv(x, rb, L.cw, out, residual=identity if L.residual else None)
+            if L.residual:
+                identity = None
+            x = out
+        dense = st["dense"]
+        dense.zero_()
+        core.sparse_to_dense(x, st["final_level"], out=dense)
+        return dense
+
+    def last_levels(self):
+        """(level, rulebook) pairs of the most recent run, for tests / roofline accounting."""
+        return [(rb.out_level, rb, L) for (L, rb, _b) in self._state["steps"]]

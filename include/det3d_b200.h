@@ -1,0 +1,192 @@
+/*
+ * det3d_b200 -- C ABI of the B200-native point-cloud inference hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / a CUDA
+ * stream (as void*), returns an int status (0 = D3B_OK), never calls exit(),
+ * never allocates device memory and never synchronises the host: the caller
+ * owns every buffer (sizes come from the *_workspace_bytes() queries) and the
+ * data-dependent row counts stay in device memory (`int*` count arguments).
+ *
+ * The reference (V2AI/Det3D) has no C/FFI plugin boundary for this path; its
+ * operator API is Python.  Each entry point below names the reference
+ * interface it stands behind (paths relative to the Det3D repository root).
+ * INTEGRATION.md shows the ctypes binding a Det3D maintainer would add.
+ */
+#ifndef DET3D_B200_H_
+#define DET3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+#define D3B_OK 0
+#define D3B_ERR_INVALID_ARG 1   /* null pointer, negative size, unsupported shape */
+#define D3B_ERR_CUDA 2          /* a CUDA runtime call failed: see d3b_last_error() */
+#define D3B_ERR_UNSUPPORTED 3   /* channel count / kernel size not built          */
+#define D3B_ERR_WORKSPACE 4     /* workspace too small                            */
+
+/* Human-readable text of the last error raised on the calling thread. */
+const char* d3b_last_error(void);
+/* ABI version; bumped whenever a signature changes. */
+int d3b_abi_version(void);
+/* Number of kernels this library has launched since load (process-wide);
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+unsigned long long d3b_launch_count(void);
+
+/* ========================================================================= *
+ * 1. Voxelizer
+ *    replaces det3d/ops/point_cloud/point_cloud_ops.py:112-184
+ *    (points_to_voxel) + :7-55 (_points_to_voxel_reverse_kernel), the
+ *    batch-index prepend of det3d/torchie/parallel/collate.py:130-137 and the
+ *    per-voxel mean of det3d/models/readers/voxel_encoder.py:206-211.
+ * ========================================================================= */
+typedef struct {
+  float voxel_size[3];   /* x, y, z                                      */
+  float range_min[3];    /* x, y, z lower bound of point_cloud_range     */
+  int32_t grid[3];       /* x, y, z cells = round((hi - lo) / voxel_size) */
+  int32_t ndim;          /* floats per point (>= 3)                      */
+  int32_t max_points;    /* max points kept per voxel                    */
+  int32_t max_voxels;    /* max voxels per cloud (the reference `break`) */
+} d3b_voxel_cfg;
+
+/* Bytes of scratch needed to voxelize `batch` clouds holding n_points_total
+ * points in one call. */
+size_t d3b_voxelize_workspace_bytes(const d3b_voxel_cfg* cfg, int32_t n_points_total,
+                                    int32_t batch);
+
+/* points        [n_total, ndim] f32 device, clouds concatenated
+ * cloud_offsets [batch + 1] i32 HOST: cloud b owns points [off[b], off[b+1])
+ * voxels        [batch*max_voxels, max_points, ndim] f32 device, or NULL
+ * coors         [batch*max_voxels, 4] i32 device (batch, z, y, x)
+ * num_points    [batch*max_voxels] i32 device
+ * mean_feats    [batch*max_voxels, ndim] f32 device, or NULL
+ * voxel_counts  [batch + 1] i32 device: [b] = voxels of cloud b, [batch] = total.
+ * Rows of all clouds are written back to back (cloud 0 first); only the
+ * first voxel_counts[batch] rows of each output are defined. */
+int d3b_voxelize(const d3b_voxel_cfg* cfg, const float* points, const int32_t* cloud_offsets,
+                 int32_t batch, float* voxels, int32_t* coors, int32_t* num_points,
+                 float* mean_feats, int32_t* voxel_counts, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* ========================================================================= *
+ * 2. Rulebook (sparse-convolution index maps)
+ *    replaces spconv v1.x `get_indice_pairs` as called by SubMConv3d /
+ *    SparseConv3d at det3d/models/backbones/scn.py:106-157,323-355
+ *    (spconv is an un-vendored dependency of the reference).
+ *
+ *    The map is output-stationary: nbr[k * row_cap + o] is the input row
+ *    feeding output row o through kernel offset k, or -1.  k enumerates
+ *    (kz, ky, kx) row-major.  tile_mask[o / 128] has bit k set when any of
+ *    the 128 rows of that tile has a neighbour at offset k.
+ * ========================================================================= */
+typedef struct {
+  int32_t spatial[3];   /* D, H, W of the level                              */
+  int32_t batch;
+  /* level-0 index: open-addressing hash (key -> row)                         */
+  uint64_t* hash_keys;  /* [hash_cap] , NULL when the level uses the bitmap   */
+  int32_t* hash_vals;   /* [hash_cap]                                         */
+  int32_t hash_cap;     /* power of two                                       */
+  /* strided-level index: occupancy bitmap + exclusive popcount prefix        */
+  uint32_t* bitmap;     /* [n_words]                                          */
+  int32_t* word_prefix; /* [n_words]                                          */
+  int64_t n_words;
+} d3b_site_index;
+
+size_t d3b_rulebook_workspace_bytes(int64_t n_words);
+
+/* Build the level-0 hash index of `coors` ([n,4] b,z,y,x; n read from *n_rows). */
+int d3b_index_build_hash(const int32_t* coors, const int32_t* n_rows, int32_t row_cap,
+                         d3b_site_index* index, void* stream);
+
+/* Submanifold rulebook: outputs == inputs (same rows, same order). */
+int d3b_rulebook_subm(const int32_t* coors, const int32_t* n_rows, int32_t row_cap,
+                      const d3b_site_index* index, const int32_t ksize[3],
+                      int32_t* nbr, uint32_t* tile_mask, void* stream);
+
+/* Strided sparse conv rulebook.  Output sites = every site reachable from an
+ * active input, in ascending linear index ((b*D+z)*H+y)*W+x.  Fills
+ * out_index (bitmap form), out_coors [out_cap,4], *n_out, nbr, tile_mask. */
+int d3b_rulebook_conv(const int32_t* in_coors, const int32_t* n_in, int32_t in_cap,
+                      const d3b_site_index* in_index, const int32_t ksize[3],
+                      const int32_t stride[3], const int32_t padding[3],
+                      d3b_site_index* out_index, int32_t* out_coors, int32_t* n_out,
+                      int32_t out_cap, int32_t* nbr, uint32_t* tile_mask, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ========================================================================= *
+ * 3. Sparse convolution (gather -> contraction -> fused epilogue)
+ *    replaces spconv v1.x `indice_conv` (gather, torch.mm, scatter-add) plus
+ *    the BatchNorm1d(eval) / ReLU / residual that follow it in
+ *    det3d/models/backbones/scn.py:73-89,106-157.
+ *
+ *    out[o,:] = act( (sum_k in[nbr[k][o],:] . W[k] + bias) * scale + shift
+ *                    + residual[o,:] )
+ * ========================================================================= */
+#define D3B_ALGO_SIMT 0   /* fp32 FFMA                                      */
+#define D3B_ALGO_TC 1     /* tcgen05 3xTF32 (fp32-equivalent), TMEM accum    */
+
+typedef struct {
+  int32_t c_in, c_out, k_vol;    /* k_vol = kd*kh*kw                          */
+  const float* weight;           /* [k_vol, c_in, c_out] f32 (spconv layout)  */
+  const float* weight_packed;    /* D3B_ALGO_TC operand image, see below      */
+  const float* bias;             /* [c_out] or NULL                           */
+  const float* scale;            /* [c_out] or NULL (folded BN)               */
+  const float* shift;            /* [c_out] or NULL                           */
+  const float* residual;         /* [n_out, c_out] or NULL                    */
+  int32_t relu;
+  int32_t algo;
+} d3b_conv_params;
+
+/* Size in floats / fill of the tensor-core weight image (hi/lo TF32 split,
+ * K-major 128B-swizzled tiles).  Done once per layer at model load. */
+size_t d3b_conv_packed_weight_floats(int32_t c_in, int32_t c_out, int32_t k_vol);
+int d3b_conv_pack_weight(const float* weight_dev, int32_t c_in, int32_t c_out, int32_t k_vol,
+                         float* packed_dev, void* stream);
+
+int d3b_sparse_conv(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask,
+                    const int32_t* n_out, int32_t out_cap, const d3b_conv_params* p,
+                    float* feat_out, void* stream);
+
+/* .dense(): rows -> zero-initialised [B, C, D, H, W] (caller zero-fills `out`).
+ * replaces SparseConvTensor.dense() at scn.py:192,365. */
+int d3b_sparse_to_dense(const float* feat, const int32_t* coors, const int32_t* n_rows,
+                        int32_t row_cap, int32_t channels, const int32_t spatial[3],
+                        int32_t batch, float* out, void* stream);
+
+/* ========================================================================= *
+ * 4. Rotated-box BEV IoU / NMS
+ * ========================================================================= */
+#define D3B_BOX_XYXYR 0   /* [x1,y1,x2,y2,ry]: det3d/ops/iou3d/src/iou3d_kernel.cu:108-221 */
+#define D3B_BOX_XYWLR 1   /* [cx,cy,w,l,r]  : det3d/ops/nms/nms_cpu.py:34-45 + nms_cpu.h:73-169 */
+
+/* Pairwise rotated IoU (mode 0) or overlap area (mode 1), out [na, nb].
+ * replaces boxes_iou_bev_gpu / boxes_overlap_bev_gpu, det3d/ops/iou3d/src/iou3d.cpp:31-71 */
+int d3b_boxes_iou_bev(const float* boxes_a, int32_t na, const float* boxes_b, int32_t nb,
+                      int32_t mode, float* out, void* stream);
+
+size_t d3b_nms_workspace_bytes(int32_t n_cap);
+
+/* Greedy NMS over boxes already sorted by descending score.
+ * fmt = D3B_BOX_XYXYR: suppress when iou >  thresh   (iou3d.cpp:73-120, nms_gpu)
+ * fmt = D3B_BOX_XYWLR: suppress when iou >= thresh and the axis-aligned hulls
+ *                      overlap                         (nms_cpu.h:73-169)
+ * n_boxes may be a device count (n_boxes_dev != NULL, bounded by n_cap).
+ * keep_idx [min(n_cap, max_keep)] i64 device receives kept positions in
+ * ascending order, keep_count [1] i32 device their number (<= max_keep). */
+int d3b_rotate_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev, int32_t fmt,
+                   float thresh, int32_t max_keep, int64_t* keep_idx, int32_t* keep_count,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Axis-aligned variant. replaces nms_normal_gpu, iou3d.cpp:123-170. */
+int d3b_normal_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev, float thresh,
+                   int32_t max_keep, int64_t* keep_idx, int32_t* keep_count, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DET3D_B200_H_ */
