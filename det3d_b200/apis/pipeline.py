@@ -1,0 +1,96 @@
+"""End-to-end, device-resident inference: raw points -> detections.
+
+The reference splits this path between DataLoader worker processes (numba voxelizer,
+per-sample CPU anchor generation, numpy collate; det3d/datasets/pipelines/preprocess.py:
+259-304,346-378, det3d/torchie/parallel/collate.py:90-150), the GPU model
+(det3d/models/detectors/voxelnet.py:30-52) and a CPU NMS (core/bbox/box_torch_ops.py:
+528-549).  `InferencePipeline` keeps the same stages and the same model objects (built
+from an unmodified Det3D config through the registries) but runs every stage on the GPU
+with fixed-shape buffers: points are voxelized for the whole batch in one call with the
+batch index and the VoxelFeatureExtractorV3 mean fused in, anchors are generated once
+and cached on the device, and detections come back as fixed-shape tensors.
+"""
+import numpy as np
+import torch
+
+from det3d_b200.core.anchor.anchor_generator import anchors_for_tasks
+from det3d_b200.models import build_detector
+from det3d_b200.ops.point_cloud.voxelize import Voxelizer
+
+
+class InferencePipeline:
+    def __init__(self, cfg, model=None, device="cuda", strict_fp32=True):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if model is None:
+            model = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+        self.model = model.to(self.device).eval()
+        vg = cfg.voxel_generator
+        self.voxelizer = Voxelizer(vg["voxel_size"], vg["range"], vg["max_points_in_voxel"], vg["max_voxel_num"],
+                                   want_voxels=False, want_mean=True)
+        self.grid_size = self.voxelizer.grid_size
+        self.num_point_features = int(cfg.model["reader"].get("num_input_features", 4))
+        out_size_factor = cfg.assigner["out_size_factor"] if "assigner" in cfg else 8
+        anchors = anchors_for_tasks(cfg.target_assigner, self.grid_size, out_size_factor)
+        self._anchors = [torch.from_numpy(a).to(self.device) for a in anchors]
+        self._anchor_cache = {}
+        self.strict_fp32 = strict_fp32
+
+    def anchors(self, batch):
+        a = self._anchor_cache.get(batch)
+        if a is None:
+            a = self._anchor_cache[batch] = [t.unsqueeze(0).expand(batch, -1, -1).contiguous() for t in self._anchors]
+        return a
+
+    @torch.no_grad()
+    def forward_device(self, points, offsets):
+        """points [N_total, ndim] f32 on the device, offsets host list -> fixed-shape detections."""
+        batch = len(offsets) - 1
+        vox = self.voxelizer(points, offsets)
+        example = dict(
+            voxels=vox["mean"], coordinates=vox["coors"], num_points=vox["num_points"],
+            num_voxels=[None] * batch, shape=[self.grid_size], anchors=self.anchors(batch),
+            n_voxels_dev=vox["counts"][batch:batch + 1],
+        )
+        prev = torch.backends.cudnn.allow_tf32
+        if self.strict_fp32:
+            torch.backends.cudnn.allow_tf32 = False
+        try:
+            det = self.model(example, return_loss=False, device_output=True)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        det["voxel_counts"] = vox["counts"]
+        return det
+
+    @staticmethod
+    def pack(det):
+        """-> one [B, D, nd+3] f32 tensor: box, score, label, valid (the D2H / all-gather payload)."""
+        return torch.cat([det["boxes"], det["scores"].unsqueeze(-1), det["labels"].float().unsqueeze(-1),
+                          det["valid"].float().unsqueeze(-1)], dim=-1).contiguous()
+
+    @torch.no_grad()
+    def infer_host(self, clouds, pinned_out=None):
+        """clouds: list of pinned (or plain) host float32 tensors [N_i, ndim].
+        H2D copy, forward, D2H of the packed detections.  Returns a host tensor [B, D, nd+3]."""
+        offsets = [0]
+        for c in clouds:
+            offsets.append(offsets[-1] + c.shape[0])
+        ndim = clouds[0].shape[1]
+        pts = torch.empty((offsets[-1], ndim), dtype=torch.float32, device=self.device)
+        for c, a, b in zip(clouds, offsets[:-1], offsets[1:]):
+            pts[a:b].copy_(c, non_blocking=True)
+        packed = self.pack(self.forward_device(pts, offsets))
+        if pinned_out is None:
+            pinned_out = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+        pinned_out.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pinned_out
+
+    @staticmethod
+    def unpack(packed_host):
+        """host [B, D, nd+3] -> list of dict(box3d_lidar, scores, label_preds) per sample."""
+        out = []
+        for row in packed_host:
+            m = row[:, -1] > 0.5
+            out.append(dict(box3d_lidar=row[m, :-3], scores=row[m, -3], label_preds=row[m, -2].long()))
+        return out

@@ -1,0 +1,25 @@
+"""Box coders needed at config-load / predict time.
+
+GroundBox3dCoderTorch mirrors det3d/core/bbox/box_coders.py:32-44,100-109:
+`.code_size`, `.n_dim`, `.decode_torch(encodings, anchors)`.  Encoding (training
+target assignment) is out of scope for the inference hot path.
+"""
+from . import box_torch_ops
+
+
+class GroundBox3dCoderTorch:
+    def __init__(self, linear_dim=False, vec_encode=False, n_dim=7, norm_velo=False):
+        self.linear_dim = linear_dim
+        self.vec_encode = vec_encode
+        self.norm_velo = norm_velo
+        self.n_dim = n_dim
+
+    @property
+    def code_size(self):
+        return self.n_dim + 1 if self.vec_encode else self.n_dim
+
+    def decode_torch(self, boxes, anchors):
+        return box_torch_ops.second_box_decode(boxes, anchors, self.vec_encode, smooth_dim=self.linear_dim)
+
+    def encode_torch(self, boxes, anchors):
+        raise NotImplementedError("box encoding is training-only; det3d_b200 covers the inference path")

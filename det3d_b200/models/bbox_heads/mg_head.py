@@ -1,0 +1,209 @@
+"""MultiGroupHead: per-task 1x1 conv heads + device-resident `predict`.
+
+Constructor, parameter names (`tasks.<i>.conv_box|conv_cls|conv_dir`), `forward` output
+dicts and `predict(example, preds_dicts, test_cfg)` results follow
+det3d/models/bbox_heads/mg_head.py:198-230, 386-533, 697-1085.  What changes is *where*
+post-processing runs: the reference loops over samples in Python and ships the top-1000
+boxes to a CPU NMS (box_torch_ops.py:537-541); here anchor decode, sigmoid, score
+filter, top-k, rotated NMS (csrc/nms.cu), direction fix and range mask all stay on the
+GPU with fixed-shape buffers, and `predict` only synchronises once, at the end, to
+slice the variable-length results the API promises.  Loss code is training-only and
+out of scope.
+"""
+import logging
+
+import numpy as np
+import torch
+from torch import nn
+
+from det3d_b200 import _lib
+from det3d_b200.ops.nms import nms_ops
+
+from ..builder import build_loss
+from ..registry import HEADS
+
+
+@HEADS.register_module
+class Head(nn.Module):
+    def __init__(self, num_input, num_pred, num_cls, use_dir=False, num_dir=0, header=True, name="",
+                 focal_loss_init=False, **kwargs):
+        super().__init__(**kwargs)
+        self.use_dir = use_dir
+        self.conv_box = nn.Conv2d(num_input, num_pred, 1)
+        self.conv_cls = nn.Conv2d(num_input, num_cls, 1)
+        if self.use_dir:
+            self.conv_dir = nn.Conv2d(num_input, num_dir, 1)
+
+    def forward(self, x):
+        out = {
+            "box_preds": self.conv_box(x).permute(0, 2, 3, 1).contiguous(),
+            "cls_preds": self.conv_cls(x).permute(0, 2, 3, 1).contiguous(),
+        }
+        if self.use_dir:
+            out["dir_cls_preds"] = self.conv_dir(x).permute(0, 2, 3, 1).contiguous()
+        return out
+
+
+@HEADS.register_module
+class MultiGroupHead(nn.Module):
+    def __init__(self, mode="3d", in_channels=[128], norm_cfg=None, tasks=[], weights=[], num_classes=[1],
+                 box_coder=None, with_cls=True, with_reg=True, reg_class_agnostic=False,
+                 encode_background_as_zeros=True, loss_norm=None, loss_cls=None, use_sigmoid_score=True,
+                 loss_bbox=None, encode_rad_error_by_sin=True, loss_aux=None, direction_offset=0.0,
+                 name="rpn", logger=None):
+        super().__init__()
+        assert with_cls or with_reg
+        num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.num_anchor_per_locs = [2 * n for n in num_classes]
+        self.box_coder = box_coder
+        self.with_cls, self.with_reg = with_cls, with_reg
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.reg_class_agnostic = reg_class_agnostic
+        self.encode_rad_error_by_sin = encode_rad_error_by_sin
+        self.encode_background_as_zeros = encode_background_as_zeros
+        self.use_sigmoid_score = use_sigmoid_score
+        self.box_n_dim = box_coder.code_size
+        self.anchor_dim = box_coder.n_dim
+        if loss_cls is not None:
+            self.loss_cls = build_loss(loss_cls)
+        if loss_bbox is not None:
+            self.loss_reg = build_loss(loss_bbox)
+        if loss_aux is not None:
+            self.loss_aux = build_loss(loss_aux)
+        self.loss_norm = loss_norm
+        self.logger = logger or logging.getLogger("MultiGroupHead")
+        self.use_direction_classifier = loss_aux is not None
+        self.direction_offset = direction_offset if loss_aux else 0.0
+        self.bev_only = mode == "bev"
+
+        self.tasks = nn.ModuleList()
+        for n_cls, n_anchor in zip(num_classes, self.num_anchor_per_locs):
+            num_cls = n_anchor * n_cls if encode_background_as_zeros else n_anchor * (n_cls + 1)
+            code = box_coder.code_size - 2 if self.bev_only else box_coder.code_size
+            self.tasks.append(Head(in_channels, n_anchor * code, num_cls, use_dir=self.use_direction_classifier,
+                                   num_dir=n_anchor * 2 if self.use_direction_classifier else None, header=False))
+        self.logger.info("Finish MultiGroupHead Initialization")
+
+    def init_weights(self, pretrained=None):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        return [task(x) for task in self.tasks]
+
+    def loss(self, example, preds_dicts, **kwargs):
+        raise NotImplementedError("training is out of scope for det3d_b200 (inference hot path only)")
+
+    # ------------------------------------------------------------------ predict
+    def _task_device_detections(self, task_id, test_cfg, cls_preds, reg_preds, dir_preds):
+        """One task, whole batch, fixed shapes, no host sync.
+
+        cls_preds [B,A,C] logits, reg_preds [B,A,7|9] decoded boxes, dir_preds [B,A,2] or None.
+        -> boxes [B,P,nd], scores [B,P], labels [B,P] int64, valid [B,P] bool  (P = nms_post_max_size)
+        """
+        nms_cfg = test_cfg["nms"] if isinstance(test_cfg, dict) else test_cfg.nms
+        if nms_cfg["use_multi_class_nms"]:
+            raise NotImplementedError("use_multi_class_nms=True is not used by the Det3D configs in scope")
+        if not (self.encode_background_as_zeros and self.use_sigmoid_score):
+            raise NotImplementedError("only sigmoid scores with background-as-zeros are on the hot path")
+        B, A, C = cls_preds.shape
+        dev = cls_preds.device
+        thr = float(test_cfg["score_threshold"])
+        pre = min(int(nms_cfg["nms_pre_max_size"]), A)
+        post = min(int(nms_cfg["nms_post_max_size"]), pre)
+        total = torch.sigmoid(cls_preds.float())
+        if C == 1:
+            top_scores = total.squeeze(-1)
+            top_labels = torch.zeros((B, A), dtype=torch.long, device=dev)
+        else:
+            top_scores, top_labels = torch.max(total, dim=-1)
+        if thr > 0.0:
+            passed = top_scores >= thr
+            ranked = torch.where(passed, top_scores, torch.full_like(top_scores, -1.0))
+        else:
+            passed = torch.ones_like(top_scores, dtype=torch.bool)
+            ranked = top_scores
+        sel_scores, sel_idx = torch.topk(ranked, k=pre, dim=1)           # descending
+        n_valid = torch.minimum(passed.sum(dim=1), torch.tensor(pre, device=dev)).to(torch.int32)
+        reg = reg_preds.float()
+        nd = reg.shape[-1]
+        cand = torch.gather(reg, 1, sel_idx.unsqueeze(-1).expand(B, pre, nd))    # [B,pre,nd]
+        boxes = torch.zeros((B, post, nd), dtype=torch.float32, device=dev)
+        scores = torch.zeros((B, post), dtype=torch.float32, device=dev)
+        labels = torch.zeros((B, post), dtype=torch.long, device=dev)
+        valid = torch.zeros((B, post), dtype=torch.bool, device=dev)
+        use_rot = bool(nms_cfg["use_rotate_nms"])
+        slot = torch.arange(post, device=dev)
+        for b in range(B):
+            if use_rot:
+                nms_boxes = cand[b][:, [0, 1, 3, 4, nd - 1]].contiguous()
+                keep_idx, keep_count = nms_ops.nms_sorted(nms_boxes, _lib.BOX_XYWLR,
+                                                          float(nms_cfg["nms_iou_threshold"]), post,
+                                                          n_dev=n_valid[b:b + 1])
+            else:
+                s, c = torch.sin(cand[b][:, nd - 1]), torch.cos(cand[b][:, nd - 1])
+                hw = 0.5 * (cand[b][:, 3] * c.abs() + cand[b][:, 4] * s.abs())
+                hl = 0.5 * (cand[b][:, 3] * s.abs() + cand[b][:, 4] * c.abs())
+                bb = torch.stack([cand[b][:, 0] - hw, cand[b][:, 1] - hl, cand[b][:, 0] + hw, cand[b][:, 1] + hl,
+                                  torch.zeros_like(hw)], dim=1).contiguous()
+                keep_idx, keep_count = nms_ops.nms_sorted(bb, _lib.BOX_XYXYR, float(nms_cfg["nms_iou_threshold"]),
+                                                          post, n_dev=n_valid[b:b + 1], axis_aligned=True)
+            ok = slot < keep_count.to(torch.long)
+            kidx = torch.where(ok, keep_idx[:post], torch.zeros_like(keep_idx[:post]))
+            src = sel_idx[b][kidx]
+            bx = cand[b][kidx]
+            if self.use_direction_classifier and dir_preds is not None:
+                dir_labels = torch.max(dir_preds[b], dim=-1)[1][src]
+                opp = ((bx[:, -1] - self.direction_offset) > 0) ^ dir_labels.bool()
+                bx = torch.cat([bx[:, :-1], (bx[:, -1] + torch.where(opp, np.pi, 0.0).to(bx.dtype)).unsqueeze(-1)], 1)
+            boxes[b] = bx
+            scores[b] = sel_scores[b][kidx]
+            labels[b] = top_labels[b][src]
+            valid[b] = ok
+        rng = test_cfg["post_center_limit_range"]
+        if rng is not None and len(rng) > 0:
+            r = torch.tensor(list(rng), dtype=torch.float32, device=dev)
+            valid &= (boxes[..., :3] >= r[:3]).all(-1) & (boxes[..., :3] <= r[3:]).all(-1)
+        return boxes, scores, labels, valid
+
+    def predict_device(self, example, preds_dicts, test_cfg):
+        """Fixed-shape, sync-free detections for the whole batch.
+
+        -> dict(boxes [B,D,nd], scores [B,D], labels [B,D] int64, valid [B,D] bool) with
+        D = sum over tasks of nms_post_max_size; labels already offset per task."""
+        outs = []
+        flag = 0
+        for task_id, preds in enumerate(preds_dicts):
+            anchors = example["anchors"][task_id]
+            B = anchors.shape[0]
+            anchors = anchors.view(B, -1, self.anchor_dim)
+            code = self.box_n_dim - 2 if self.bev_only else self.box_n_dim
+            box_preds = preds["box_preds"].view(B, -1, code)
+            n_cls = self.num_classes[task_id] if self.encode_background_as_zeros else self.num_classes[task_id] + 1
+            cls_preds = preds["cls_preds"].view(B, -1, n_cls)
+            reg = self.box_coder.decode_torch(box_preds[:, :, : self.box_coder.code_size], anchors)
+            dirs = preds["dir_cls_preds"].view(B, -1, 2) if self.use_direction_classifier else None
+            bx, sc, lb, ok = self._task_device_detections(task_id, test_cfg, cls_preds, reg, dirs)
+            outs.append((bx, sc, lb + flag, ok))
+            flag += self.num_classes[task_id]
+        return dict(boxes=torch.cat([o[0] for o in outs], 1), scores=torch.cat([o[1] for o in outs], 1),
+                    labels=torch.cat([o[2] for o in outs], 1), valid=torch.cat([o[3] for o in outs], 1))
+
+    def predict(self, example, preds_dicts, test_cfg, **kwargs):
+        """list (per sample) of dict(box3d_lidar [K,nd], scores [K], label_preds [K], metadata)."""
+        det = self.predict_device(example, preds_dicts, test_cfg)
+        B = det["boxes"].shape[0]
+        meta = example.get("metadata") if isinstance(example, dict) else None
+        if not meta:
+            meta = [None] * B
+        results = []
+        for b in range(B):
+            m = det["valid"][b]
+            results.append({"box3d_lidar": det["boxes"][b][m], "scores": det["scores"][b][m],
+                            "label_preds": det["labels"][b][m], "metadata": meta[b]})
+        return results

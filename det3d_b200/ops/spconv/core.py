@@ -19,6 +19,9 @@ from ... import _lib
 from ..._lib import ConvParams, SiteIndex
 
 TILE_M = 128
+# bench.py hook: when set to a list, every sparse_conv launch is bracketed by CUDA events
+# recorded on the launching stream and the (start, end) pair is appended here.
+PROFILE_EVENTS = None
 
 
 def _i3(v):
@@ -256,11 +259,18 @@ def sparse_conv(feat_in, rb, cw, feat_out, residual=None):
     p.residual = _lib.ptr(residual)
     p.relu = 1 if cw.relu else 0
     p.algo = cw.algo
+    events = PROFILE_EVENTS
+    if events is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     st = _lib.lib().d3b_sparse_conv(
         feat_in.data_ptr(), rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), rb.out_level.n.data_ptr(),
         rb.out_level.cap, C.byref(p), feat_out.data_ptr(), _lib.current_stream(),
     )
     _lib.check(st, "d3b_sparse_conv")
+    if events is not None:
+        ev1.record()
+        events.append((ev0, ev1))
     return feat_out
 
 

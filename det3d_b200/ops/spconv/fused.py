@@ -190,6 +190,29 @@ class FusedSparseEncoder:
         core.sparse_to_dense(x, st["final_level"], out=dense)
         return dense
 
+    def accounting(self):
+        """Algorithmic bytes / flops of the most recent run (SURVEY 8d formulas; synchronises).
+
+        per layer: bytes = N_in*Cin*4 + N_out*Cout*4 + P*8 + K*Cin*Cout*4, flops = 2*P*Cin*Cout,
+        P = rulebook pairs.  Plus the dense write B*C*D*H*W*4 reported separately."""
+        layers, tot_b, tot_f = [], 0, 0
+        pair_cache = {}
+        for L, rb, _b in self._state["steps"]:
+            n_out = int(rb.out_level.n[0].item())
+            n_in = int(rb.in_level.n[0].item())
+            key = id(rb)
+            if key not in pair_cache:
+                pair_cache[key] = int((rb.nbr[:, :n_out] >= 0).sum().item()) if n_out else 0
+            pairs = pair_cache[key]
+            cin, cout, k = L.conv.in_channels, L.conv.out_channels, rb.k_vol
+            b = n_in * cin * 4 + n_out * cout * 4 + pairs * 8 + k * cin * cout * 4
+            f = 2 * pairs * cin * cout
+            layers.append(dict(n_in=n_in, n_out=n_out, pairs=pairs, c_in=cin, c_out=cout, k_vol=k, bytes=b, flops=f,
+                               algo=L.cw.algo))
+            tot_b += b
+            tot_f += f
+        return dict(layers=layers, bytes=tot_b, flops=tot_f, dense_bytes=int(self._state["dense"].numel() * 4))
+
     def last_levels(self):
         """(level, rulebook) pairs of the most recent run, for tests / roofline accounting."""
         return [(rb.out_level, rb, L) for (L, rb, _b) in self._state["steps"]]

@@ -1,0 +1,86 @@
+"""Seeded synthetic inputs: point clouds, NMS box sets, random BN statistics."""
+import numpy as np
+
+
+def uniform_cloud(n, point_cloud_range, ndim=4, seed=0):
+    """x,y,z ~ U[lo,hi) per axis, intensity ~ U[0,1), further features 0 (worst case for dilation)."""
+    rng = np.random.default_rng(seed)
+    r = np.asarray(point_cloud_range, np.float64)
+    pts = np.zeros((n, ndim), np.float32)
+    for j in range(3):
+        pts[:, j] = rng.uniform(r[j], r[3 + j], n)
+    if ndim > 3:
+        pts[:, 3] = rng.uniform(0, 1, n)
+    return pts
+
+
+def lidar_like_cloud(n, point_cloud_range, ndim=4, seed=0):
+    """64-beam spinning-lidar look-alike: rays from a sensor 1.73 m above the ground hit the
+    ground plane or (35 %) an obstacle at 5-70 m; cropped to the range, shuffled, first n kept."""
+    rng = np.random.default_rng(seed)
+    r = np.asarray(point_cloud_range, np.float64)
+    front_only = r[0] >= 0
+    out = []
+    need = n
+    while need > 0:
+        m = max(4 * need, 4096)
+        beam = rng.integers(0, 64, m)
+        elev = np.deg2rad(-24.8 + beam * (26.8 / 63.0))
+        azim = rng.uniform(-np.pi / 4, np.pi / 4, m) if front_only else rng.uniform(-np.pi, np.pi, m)
+        h = 1.73
+        with np.errstate(divide="ignore"):
+            ground_d = np.where(elev < -1e-3, h / np.tan(-elev), np.inf)
+        obst = rng.uniform(0, 1, m) < 0.35
+        obst_d = rng.uniform(5, 70, m)
+        d = np.where(obst, np.minimum(obst_d, ground_d), ground_d)
+        ok = np.isfinite(d) & (d < 120)
+        d = np.where(ok, d, 1.0)
+        z = -h + np.where(obst & (obst_d < ground_d), rng.uniform(0, 1.6, m), 0.0) + rng.normal(0, 0.02, m)
+        x, y = d * np.cos(azim), d * np.sin(azim)
+        ok &= (x >= r[0]) & (x < r[3]) & (y >= r[1]) & (y < r[4]) & (z >= r[2]) & (z < r[5])
+        p = np.zeros((int(ok.sum()), ndim), np.float32)
+        p[:, 0], p[:, 1], p[:, 2] = x[ok], y[ok], z[ok]
+        if ndim > 3:
+            p[:, 3] = rng.uniform(0, 1, p.shape[0])
+        out.append(p)
+        need -= p.shape[0]
+    pts = np.concatenate(out, 0)
+    rng.shuffle(pts)
+    return np.ascontiguousarray(pts[:n])
+
+
+def nms_boxes_xyxyr(n, seed=0, clustered=False, extent=100.0):
+    """[n,5] x1,y1,x2,y2,ry + distinct scores."""
+    rng = np.random.default_rng(seed)
+    if clustered:
+        centres = rng.uniform(0, extent, (max(n // 50, 1), 2))
+        c = centres[rng.integers(0, centres.shape[0], n)] + rng.normal(0, 3.0, (n, 2))
+    else:
+        c = rng.uniform(0, extent, (n, 2))
+    w = rng.uniform(1.5, 2.5, n)
+    l = rng.uniform(3.5, 5.0, n)
+    ry = rng.uniform(-np.pi, np.pi, n)
+    boxes = np.stack([c[:, 0] - w / 2, c[:, 1] - l / 2, c[:, 0] + w / 2, c[:, 1] + l / 2, ry], 1).astype(np.float32)
+    scores = (rng.permutation(n).astype(np.float32) + 1) / n
+    return boxes, scores
+
+
+def xyxyr_to_xywlr(boxes):
+    b = np.asarray(boxes, np.float32)
+    return np.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1], b[:, 4]],
+                    1).astype(np.float32)
+
+
+def randomize_bn_(model, seed=0):
+    """Random running stats / affine so BN folding is exercised (mean~N(0,.1), var~U[.5,1.5])."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            if m.weight is not None:
+                m.weight.data.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    return model
