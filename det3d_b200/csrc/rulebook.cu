@@ -246,15 +246,23 @@ rb_scan_emit(const unsigned int* __restrict__ bitmap, long long n_words,
     if (base + j >= n_words) break;
     word_prefix[base + j] = rank;
     unsigned int bits = w[j];
+    if (bits == 0u) continue;
+    // decompose the word's first cell once (64-bit divisions), then walk bits with carries
+    unsigned long long lin = (unsigned long long)(base + j) << 5;
+    const int x0 = (int)(lin % out.W); lin /= out.W;
+    const int y0 = (int)(lin % out.H); lin /= out.H;
+    const int z0 = (int)(lin % out.D);
+    const int b0 = (int)(lin / out.D);
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
       if (rank < out_cap) {
-        unsigned long long lin = ((unsigned long long)(base + j) << 5) + b;
-        const int x = (int)(lin % out.W); lin /= out.W;
-        const int y = (int)(lin % out.H); lin /= out.H;
-        const int z = (int)(lin % out.D); lin /= out.D;
-        *reinterpret_cast<int4*>(out_coors + (size_t)rank * 4) = make_int4((int)lin, z, y, x);
+        int x = x0 + b, y = y0, z = z0, bb = b0;
+        while (x >= out.W) {
+          x -= out.W;
+          if (++y >= out.H) { y = 0; if (++z >= out.D) { z = 0; ++bb; } }
+        }
+        *reinterpret_cast<int4*>(out_coors + (size_t)rank * 4) = make_int4(bb, z, y, x);
       }
       ++rank;
     }

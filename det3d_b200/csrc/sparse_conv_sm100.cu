@@ -1,11 +1,402 @@
-// placeholder (tensor-core kernel lands next)
+// Output-stationary sparse convolution on the 5th-gen tensor cores (sm_100a).
+//
+//   out[o,:] = act((sum_k in[nbr[k][o],:] . W[k] + bias) * scale + shift + residual[o,:])
+//
+// The reference computes this contraction as fp32 SGEMMs (spconv v1.x indice_conv:
+// per offset gather -> torch.mm -> scatter-add; call sites
+// det3d/models/backbones/scn.py:106-157).  Here one CTA owns 128 output rows; for
+// every kernel offset that has a neighbour in the tile (tile_mask) and every 32-channel
+// slice of C_in, four producer warps gather the 128 input rows straight from global/L2
+// into a K-major, 128B-swizzled shared-memory tile, and one thread issues
+// tcgen05.mma.kind::tf32 (M=128, N=C_out, K=8) accumulating in TMEM.  No scatter, no
+// atomics; BN/bias/residual/ReLU are applied on the way out of TMEM.
+//
+// fp32-equivalent accuracy ("3xTF32"): every fp32 operand x is split exactly into
+//   hi = x with the low 13 mantissa bits cleared (a TF32 number), lo = x - hi (13 bits),
+// and D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi with fp32 accumulation; the dropped
+// lo.lo term is O(2^-22) relative.  Activations are split in registers while being
+// gathered; weights are split once at load time by d3b_conv_pack_weight, which also
+// lays them out as the exact shared-memory image (K-major, 128B swizzle) so that one
+// cp.async.bulk (TMA) per stage brings the B operand in.
+//
+// Pipeline: NSTAGE-deep ring of {A_hi, A_lo, B_hi, B_lo} tiles guarded by full/empty
+// mbarriers; producers -> (generic-proxy stores + fence.proxy.async + arrive),
+// TMA -> complete_tx, MMA thread -> tcgen05.commit on the empty barrier.  Persistent
+// grid (<= one CTA per SM), tile loop with an accumulator full/empty barrier pair.
+//
+// Algorithmic bytes per layer: N_in*C_in*4 + N_out*C_out*4 + P*8 + K*C_in*C_out*4
+// (SURVEY 8d); tensor work issued: 3 * 2 * 128 * C_out * 32 flop per (tile, offset, slice).
 #include "common.cuh"
+
 namespace d3b {
-int sparse_conv_tc(const float*, const int32_t*, const uint32_t*, const int32_t*, int32_t,
-                   const d3b_conv_params*, float*, cudaStream_t) {
-  set_error("tensor-core sparse conv not built");
-  return D3B_ERR_UNSUPPORTED;
+
+constexpr int kTcTileM = 128;
+constexpr int kTcKc = 32;               // channels per stage = one 128-byte swizzle row
+constexpr int kTcThreads = 160;         // warps 0-3: gather + epilogue, warp 4: TMEM alloc + MMA issue
+constexpr int kABytes = kTcTileM * 128; // one A tile (hi or lo)
+
+// ---- PTX wrappers --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-extern "C" size_t d3b_conv_packed_weight_floats(int32_t, int32_t, int32_t) { return 0; }
-extern "C" int d3b_conv_pack_weight(const float*, int32_t, int32_t, int32_t, float*, void*) { return D3B_ERR_UNSUPPORTED; }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version 1<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of (row, 16-byte chunk) inside a K-major SW128 tile
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;  // exact: the low 13 mantissa bits
+}
+
+template <int COUT>
+struct TcCfg {
+  static constexpr int kBBytes = COUT * 128;                       // one B tile (hi or lo)
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (COUT >= 128) ? 3 : 4;
+  static constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
+                 const unsigned int* __restrict__ tile_mask, const int* __restrict__ n_out_p, int out_cap,
+                 int c_in, int n_kb, const float* __restrict__ packed, const float* __restrict__ bias,
+                 const float* __restrict__ scale, const float* __restrict__ shift,
+                 const float* __restrict__ residual, int relu, float* __restrict__ feat_out) {
+  using Cfg = TcCfg<COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t accum_full = bar_base + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_empty = bar_base + 8u * (2 * Cfg::kStages + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_out = min(*n_out_p, out_cap);
+  const int n_tiles = (n_out + kTcTileM - 1) / kTcTileM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 128 + 1);  // 128 gather threads + the expect_tx arrive
+      mbar_init(empty_bar(s), 1);       // tcgen05.commit
+    }
+    mbar_init(accum_full, 1);
+    mbar_init(tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  uint32_t it = 0;        // pipeline slot counter (same sequence in producer and MMA roles)
+  uint32_t tile_it = 0;   // accumulator phase counter
+
+  if (warp < 4) {
+    // ===================== gather producers, then epilogue =====================
+    const int g = lane >> 3, c = lane & 7;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row0 = tile * kTcTileM;
+      unsigned int mask = tile_mask[tile];
+      const bool any = mask != 0;
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int my_row = row0 + warp * 32 + lane;
+        const int my_nbr = my_row < n_out ? nbr[(size_t)k * out_cap + my_row] : -1;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          uint8_t* stage = smem_gen + (size_t)s * Cfg::kStageBytes;
+          if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
+            tma_bulk_g2s(smem_base + s * Cfg::kStageBytes + 2 * kABytes,
+                         packed + ((size_t)k * n_kb + kb) * (2 * Cfg::kBBytes / 4), 2 * Cfg::kBBytes, full_bar(s));
+          }
+          float4 v[8];
+          const int ch = kb * kTcKc + c * 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int src = __shfl_sync(0xffffffffu, my_nbr, 4 * j + g);
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src >= 0 && ch < c_in) v[j] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src * c_in + ch));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = warp * 32 + 4 * j + g;
+            float4 hi, lo;
+            split_tf32(v[j].x, hi.x, lo.x);
+            split_tf32(v[j].y, hi.y, lo.y);
+            split_tf32(v[j].z, hi.z, lo.z);
+            split_tf32(v[j].w, hi.w, lo.w);
+            const uint32_t off = sw128_offset(row, c);
+            *reinterpret_cast<float4*>(stage + off) = hi;
+            *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
+          }
+          fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
+          mbar_arrive(full_bar(s));
+        }
+      }
+      // ---- epilogue: TMEM -> registers -> fused BN/bias/residual/ReLU -> global ----
+      const int o = row0 + warp * 32 + lane;
+      if (any) {
+        mbar_wait(accum_full, tile_it & 1u);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t r[16];
+        if (any) {
+          tc_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) r[q] = 0u;
+        }
+        if (o < n_out) {
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            float4 val = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
+                                     __uint_as_float(r[q + 3]));
+            const int col = c0 + q;
+            if (bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+              val.x += b4.x; val.y += b4.y; val.z += b4.z; val.w += b4.w;
+            }
+            if (scale) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + col));
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(shift + col));
+              val.x = fmaf(val.x, s4.x, t4.x); val.y = fmaf(val.y, s4.y, t4.y);
+              val.z = fmaf(val.z, s4.z, t4.z); val.w = fmaf(val.w, s4.w, t4.w);
+            }
+            if (residual) {
+              const float4 q4 = __ldg(reinterpret_cast<const float4*>(residual + (size_t)o * COUT + col));
+              val.x += q4.x; val.y += q4.y; val.z += q4.z; val.w += q4.w;
+            }
+            if (relu) {
+              val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(feat_out + (size_t)o * COUT + col) = val;
+          }
+        }
+      }
+      if (any) {
+        tc_fence_before();
+        mbar_arrive(tmem_empty);   // accumulator drained: the MMA thread may start the next tile
+        ++tile_it;
+      }
+    }
+  } else {
+    // ===================== MMA issuer (one elected lane of warp 4) =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(kTcTileM, COUT);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      unsigned int mask = tile_mask[tile];
+      if (mask == 0) continue;
+      mbar_wait(tmem_empty, (tile_it & 1u) ^ 1u);
+      tc_fence_after();
+      uint32_t accumulate = 0;
+      while (mask) {
+        mask &= mask - 1;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
+            const uint32_t a_lo = a_hi + kABytes;
+            const uint32_t b_hi = a_lo + kABytes;
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+            for (int kk = 0; kk < kTcKc / 8; ++kk) {
+              const uint32_t adv = kk * 32;  // 8 tf32 = 32 bytes along K inside the swizzle row
+              tc_mma_tf32(tmem_d, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, accumulate);
+              tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
+              tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
+              accumulate = 1u;
+            }
+            tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+          }
+          __syncwarp();
+          accumulate = 1u;
+        }
+      }
+      if (lane == 0) tc_commit(accum_full);
+      __syncwarp();
+      ++tile_it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- weight image ------------------------------------------------------------------------
+// packed[k][kb][part][n][swizzled 32 floats], part 0 = hi, 1 = lo; zero beyond c_in.
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, int c_in, int c_out, int k_vol, int n_kb,
+                   float* __restrict__ packed) {
+  const long long total = (long long)k_vol * n_kb * 2 * c_out * kTcKc;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long t = e;
+    const int cc = (int)(t % kTcKc); t /= kTcKc;   // channel within the slice
+    const int n = (int)(t % c_out); t /= c_out;
+    const int part = (int)(t % 2); t /= 2;
+    const int kb = (int)(t % n_kb); t /= n_kb;
+    const int k = (int)t;
+    const int ci = kb * kTcKc + cc;
+    float x = ci < c_in ? w[((size_t)k * c_in + ci) * c_out + n] : 0.0f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    const size_t tile = (((size_t)k * n_kb + kb) * 2 + part) * (size_t)(c_out * kTcKc);
+    const uint32_t off = sw128_offset(n, cc >> 2) + (cc & 3) * 4;
+    packed[tile + off / 4] = part == 0 ? hi : lo;
+  }
+}
+
+static bool tc_shape_ok(int c_in, int c_out) {
+  const bool cin_ok = c_in == 16 || c_in == 32 || c_in == 64 || c_in == 128;
+  const bool cout_ok = c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128;
+  return cin_ok && cout_ok;
+}
+
+template <int COUT>
+static int launch_tc(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out,
+                     int32_t out_cap, const d3b_conv_params* p, float* feat_out, cudaStream_t stream) {
+  using Cfg = TcCfg<COUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int n_tiles = div_up(out_cap, kTcTileM);
+  const int grid = n_tiles < kNumSMs ? (n_tiles > 0 ? n_tiles : 1) : kNumSMs;
+  const int n_kb = (p->c_in + kTcKc - 1) / kTcKc;
+  spconv_tc_kernel<COUT><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(
+      feat_in, nbr, tile_mask, n_out, out_cap, p->c_in, n_kb, p->weight_packed, p->bias, p->scale, p->shift,
+      p->residual, p->relu, feat_out);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+int sparse_conv_tc(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out,
+                   int32_t out_cap, const d3b_conv_params* p, float* feat_out, cudaStream_t stream) {
+  if (!tc_shape_ok(p->c_in, p->c_out)) {
+    set_error("tensor-core sparse conv: unsupported C_in=%d C_out=%d", p->c_in, p->c_out);
+    return D3B_ERR_UNSUPPORTED;
+  }
+  D3B_REQUIRE(p->weight_packed, "tensor-core sparse conv: weight_packed is null (call d3b_conv_pack_weight)");
+  D3B_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "scale and shift must be given together");
+  switch (p->c_out) {
+    case 16: return launch_tc<16>(feat_in, nbr, tile_mask, n_out, out_cap, p, feat_out, stream);
+    case 32: return launch_tc<32>(feat_in, nbr, tile_mask, n_out, out_cap, p, feat_out, stream);
+    case 64: return launch_tc<64>(feat_in, nbr, tile_mask, n_out, out_cap, p, feat_out, stream);
+    default: return launch_tc<128>(feat_in, nbr, tile_mask, n_out, out_cap, p, feat_out, stream);
+  }
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+
+extern "C" size_t d3b_conv_packed_weight_floats(int32_t c_in, int32_t c_out, int32_t k_vol) {
+  if (!tc_shape_ok(c_in, c_out) || k_vol < 1 || k_vol > 32) return 0;
+  const int n_kb = (c_in + kTcKc - 1) / kTcKc;
+  return (size_t)k_vol * n_kb * 2 * c_out * kTcKc;
+}
+
+extern "C" int d3b_conv_pack_weight(const float* weight_dev, int32_t c_in, int32_t c_out, int32_t k_vol,
+                                    float* packed_dev, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(weight_dev && packed_dev, "d3b_conv_pack_weight: null argument");
+  const size_t n = d3b_conv_packed_weight_floats(c_in, c_out, k_vol);
+  if (n == 0) {
+    set_error("d3b_conv_pack_weight: unsupported C_in=%d C_out=%d k_vol=%d", c_in, c_out, k_vol);
+    return D3B_ERR_UNSUPPORTED;
+  }
+  const int n_kb = (c_in + kTcKc - 1) / kTcKc;
+  pack_weight_kernel<<<grid_for((long long)n, 256), 256, 0, stream>>>(weight_dev, c_in, c_out, k_vol, n_kb, packed_dev);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}

@@ -79,6 +79,10 @@ vox_insert(const VoxParams p, const float* __restrict__ points, unsigned long lo
 }
 
 // ---- B: rank voxels by first point (one CTA per cloud) -------------------------
+// Each thread owns kRankItems consecutive points per pass so the two dependent loads
+// (pslot -> first) of a whole 8k-point chunk are in flight together.
+constexpr int kRankItems = 8;
+
 __global__ void __launch_bounds__(1024)
 vox_rank(const VoxParams p, const int* __restrict__ first, const int* __restrict__ pslot,
          int* __restrict__ vid, int* __restrict__ vslot, int* __restrict__ cut,
@@ -91,15 +95,23 @@ vox_rank(const VoxParams p, const int* __restrict__ first, const int* __restrict
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { running = 0; cut_s = end; }
   __syncthreads();
-  for (int base = beg; base < end; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    int slot = -1, flag = 0;
-    if (i < end) {
-      slot = pslot[i];
-      flag = (slot >= 0 && first[slot] == i) ? 1 : 0;
+  for (int base = beg; base < end; base += blockDim.x * kRankItems) {
+    const int i0 = base + threadIdx.x * kRankItems;
+    int slot[kRankItems], fst[kRankItems];
+#pragma unroll
+    for (int j = 0; j < kRankItems; ++j) slot[j] = (i0 + j < end) ? pslot[i0 + j] : -1;
+#pragma unroll
+    for (int j = 0; j < kRankItems; ++j) fst[j] = slot[j] >= 0 ? first[slot[j]] : -1;
+    int local = 0;
+    unsigned int flags = 0;
+#pragma unroll
+    for (int j = 0; j < kRankItems; ++j) {
+      const int f = (slot[j] >= 0 && fst[j] == i0 + j) ? 1 : 0;
+      flags |= (unsigned int)f << j;
+      local += f;
     }
-    // block-wide exclusive scan of flag
-    int incl = flag;
+    // block-wide exclusive scan of the per-thread counts
+    int incl = local;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -119,15 +131,18 @@ vox_rank(const VoxParams p, const int* __restrict__ first, const int* __restrict
     __syncthreads();
     const int warp_off = warp == 0 ? 0 : warp_sums[warp - 1];
     const int chunk_total = warp_sums[31];
-    const int r = running + warp_off + incl - flag;  // exclusive rank
-    if (flag) {
+    int r = running + warp_off + incl - local;  // exclusive rank of this thread's first flagged point
+#pragma unroll
+    for (int j = 0; j < kRankItems; ++j) {
+      if (!((flags >> j) & 1u)) continue;
       if (r < p.max_voxels) {
-        vid[slot] = r;
-        vslot[b * p.max_voxels + r] = slot;
+        vid[slot[j]] = r;
+        vslot[b * p.max_voxels + r] = slot[j];
       } else {
-        vid[slot] = -1;
-        if (r == p.max_voxels) cut_s = i;  // the reference `break` fires here
+        vid[slot[j]] = -1;
+        if (r == p.max_voxels) cut_s = i0 + j;  // the reference `break` fires here
       }
+      ++r;
     }
     __syncthreads();
     if (threadIdx.x == 0) running += chunk_total;

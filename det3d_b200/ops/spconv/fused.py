@@ -164,6 +164,8 @@ class FusedSparseEncoder:
         # adopt the caller's coordinate rows (zero-copy) for this run
         coors = coors.to(torch.int32).contiguous()
         feats = features.to(torch.float32).contiguous()
+        if m == 0:  # keep pointers valid; the device row count (0) makes every kernel a no-op
+            feats = torch.zeros((1, features.shape[1]), dtype=torch.float32, device=device)
         if m > 0:
             lvl0.coors[:m].copy_(coors)
         if n_dev is None:

@@ -143,7 +143,8 @@ def _encoder_case(cls_name, cin, n, seed, spatial_xyz=(96, 112, 40), batch=2):
 def test_fused_encoder_vs_oracle(cls_name, cin, algo):
     from det3d_b200 import _lib
     model, feats, coors, input_shape, batch = _encoder_case(cls_name, cin, 6000, 3)
-    want = osp.middle_encoder_forward(model.state_dict(), feats, coors, batch, input_shape, arch=cls_name)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    want = osp.middle_encoder_forward(sd, feats, coors, batch, input_shape, arch=cls_name)
     model = model.cuda()
     if algo == "simt":
         model.fused().algo_override = _lib.ALGO_SIMT
@@ -152,7 +153,7 @@ def test_fused_encoder_vs_oracle(cls_name, cin, algo):
     assert float((got - want).abs().max()) <= TOL
     # run again with fewer live rows in the same buffers (device-side count path)
     n2 = 2500
-    want2 = osp.middle_encoder_forward(model.state_dict(), feats[:n2], coors[:n2], batch, input_shape, arch=cls_name)
+    want2 = osp.middle_encoder_forward(sd, feats[:n2], coors[:n2], batch, input_shape, arch=cls_name)
     n_dev = torch.tensor([n2], dtype=torch.int32, device="cuda")
     got2 = model(torch.from_numpy(feats).cuda(), torch.from_numpy(coors).cuda(), batch, input_shape, n_dev=n_dev).cpu()
     assert float((got2 - want2).abs().max()) <= TOL
