@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--dist", default="lidar_like", choices=["lidar_like", "uniform"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allow-tf32-rpn", action="store_true", help="let cuDNN use TF32 in the dense RPN")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-fused-bev", action="store_true", help="RPN/head through torch+cuDNN instead of the tcgen05 path")
     return ap.parse_args()
 
 
@@ -143,7 +145,10 @@ def workload_config(args, world):
     return {"workload": "SECOND kitti_car_vfev3_spmiddlefhd_rpn1 forward, 20k synthetic pts, batch=%d/GPU" % args.batch,
             "distribution": args.dist, "points_per_cloud": N_POINTS, "batch_per_gpu": args.batch,
             "global_batch": args.batch * world, "cloud_pool": N_CLOUD_POOL, "l2": "flushed (256 MiB write) between steps",
-            "parallelism": "dp%d" % world, "rpn_math": "fp32 (cudnn.allow_tf32=%s)" % bool(args.allow_tf32_rpn)}
+            "parallelism": "dp%d" % world,
+            "rpn_math": ("cuDNN fp32 (allow_tf32=%s)" % bool(args.allow_tf32_rpn)) if args.no_fused_bev
+            else "tcgen05 3xTF32 (fp32-equivalent), channels-last",
+            "cuda_graph": not args.no_graph}
 
 
 def main():
@@ -168,12 +173,15 @@ def main():
     dev = torch.device("cuda", local)
     cfg = Config.fromfile(CONFIG)
     pipe = InferencePipeline(cfg, model=build_model(cfg), device=dev, strict_fp32=not args.allow_tf32_rpn)
+    pipe.model.use_fused_bev = not args.no_fused_bev
+    use_graph = not args.no_graph
     B = args.batch
     clouds_np = make_clouds(args.dist, N_CLOUD_POOL, 1000 * rank, cfg.voxel_generator.range)
     pinned = [torch.from_numpy(c).pin_memory() for c in clouds_np]
     resident = [torch.from_numpy(c).to(dev) for c in clouds_np]
     offsets = [N_POINTS * i for i in range(B + 1)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e2e_pts = torch.empty((N_POINTS * B, 4), dtype=torch.float32, device=dev)
     out_pinned = None
 
     def batch_ids(step):
@@ -182,16 +190,17 @@ def main():
     def step_device(step):
         ids = batch_ids(step)
         pts = resident[ids[0]] if B == 1 else torch.cat([resident[i] for i in ids])
-        det = pipe.forward_device(pts, offsets)
-        return all_gather_detections(pipe.pack(det))
+        packed = pipe.forward_graphed(pts, offsets) if use_graph else pipe.pack(pipe.forward_device(pts, offsets))
+        return all_gather_detections(packed)
 
     def step_e2e(step):
         nonlocal out_pinned
         ids = batch_ids(step)
-        pts = torch.empty((N_POINTS * B, 4), dtype=torch.float32, device=dev)
+        pts = e2e_pts
         for j, i in enumerate(ids):
-            pts[j * N_POINTS:(j + 1) * N_POINTS].copy_(pinned[i], non_blocking=True)
-        gathered = all_gather_detections(pipe.pack(pipe.forward_device(pts, offsets)))
+            pts[j * N_POINTS:(j + 1) * N_POINTS].copy_(pinned[i], non_blocking=True)   # H2D from pinned memory
+        packed = pipe.forward_graphed(pts, offsets) if use_graph else pipe.pack(pipe.forward_device(pts, offsets))
+        gathered = all_gather_detections(packed)
         if out_pinned is None:
             out_pinned = torch.empty(gathered.shape, dtype=torch.float32, pin_memory=True)
         out_pinned.copy_(gathered, non_blocking=True)
@@ -204,7 +213,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, conv_events=None):
+    def timed(fn, steps, conv_events=None):  # noqa: E306
         evs = []
         barrier()
         for s in range(steps):
@@ -229,38 +238,60 @@ def main():
         step_device(s)
         step_e2e(s)
 
+    def step_eager(step):
+        ids = batch_ids(step)
+        pts = resident[ids[0]] if B == 1 else torch.cat([resident[i] for i in ids])
+        return all_gather_detections(pipe.pack(pipe.forward_device(pts, offsets)))
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
-    conv_events = []
-    ms = timed(step_device, args.steps, conv_events)
-    launches = _lib.launch_count() - launches0
+    ms = timed(step_device, args.steps)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant hand-written kernel family (sparse conv) ----------------------
+    # ---- per-kernel pass (eager launches of the SAME kernels, CUDA events around every
+    #      d3b_sparse_conv launch on the launching stream): launch count + roofline numerators ----
+    n_prof = min(args.steps, 10)
+    launches0 = _lib.launch_count()
+    conv_events = []
+    timed(step_eager, n_prof, conv_events)
+    launches_per_step = (_lib.launch_count() - launches0) / n_prof
+    torch.cuda.synchronize()
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    torch.cuda.synchronize()
-    conv_ms = sum(a.elapsed_time(b) for a, b in conv_events)
-    acct = pipe.model.backbone.fused().accounting()          # algorithmic bytes / flops of the LAST step
-    n_conv = len(conv_events)
-    per_step_convs = len(acct["layers"])
-    conv_ms_per_launch = conv_ms / max(n_conv, 1)
-    bytes_per_launch = acct["bytes"] / max(per_step_convs, 1)
-    achieved = bytes_per_launch / (conv_ms_per_launch * 1e-3) / 1e9 if conv_ms_per_launch > 0 else 0.0
-    roofline = {"kernel": "d3b sparse_conv (14 launches/step, tcgen05 3xTF32 or fp32 SIMT per layer)", "bound": "hbm",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": acct["bytes"],
-                "flops_per_step": acct["flops"], "kernel_ms_per_step": conv_ms / max(args.steps, 1),
-                "achieved_tflops": acct["flops"] / (conv_ms / max(args.steps, 1) * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
-                "share_of_step": (conv_ms / max(args.steps, 1)) / (ms / args.steps)}
+    tc_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0       # kind::tf32 runs at half the bf16 rate
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    enc = pipe.model.backbone.fused().accounting()             # algorithmic bytes / flops of the last step
+    n_enc = len(enc["layers"])
+    per_step = len(conv_events) // n_prof
+    enc_ms = sum(a.elapsed_time(b) for i, (a, b) in enumerate(conv_events) if i % per_step < n_enc) / n_prof
+    bev_ms = sum(a.elapsed_time(b) for i, (a, b) in enumerate(conv_events) if i % per_step >= n_enc) / n_prof
+    ms_step = ms / args.steps
+    achieved = enc["bytes"] / (enc_ms * 1e-3) / 1e9 if enc_ms > 0 else 0.0
+    roofline = {"kernel": "d3b spconv_tc_kernel / spconv_simt_kernel: sparse middle encoder, %d launches/step" % n_enc,
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": enc["bytes"],
+                "flops_per_step": enc["flops"], "kernel_ms_per_step": enc_ms,
+                "achieved_tflops": enc["flops"] / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else 0.0,
+                "share_of_step": enc_ms / ms_step, "timing": "CUDA events around each launch, eager pass of %d steps" % n_prof}
+    extra = {}
+    if per_step > n_enc:
+        hw = B * 200 * 176
+        bev_flops = sum(2 * hw * k * ci * co for (k, ci, co) in [(9, 128, 128)] * 6 + [(1, 128, 128), (1, 128, 32)])
+        bev_tf = bev_flops / (bev_ms * 1e-3) / 1e12 if bev_ms > 0 else 0.0
+        extra["roofline_bev"] = {"kernel": "d3b spconv_tc_kernel on the dense BEV grid (RPN 6x conv3x3 + 1x1 deblock + fused heads), "
+                                           "%d launches/step" % (per_step - n_enc),
+                                 "bound": "tensor", "achieved": bev_tf, "peak": tc_peak, "unit": "TFLOP/s",
+                                 "frac": bev_tf / tc_peak, "traffic": None,
+                                 "note": "fp32-equivalent flops; the kernel issues 3 TF32 MMAs per product (3xTF32), "
+                                         "so tensor-pipe work is 3x this; peak = measured bf16 burst / 2",
+                                 "flops_per_step": bev_flops, "kernel_ms_per_step": bev_ms, "share_of_step": bev_ms / ms_step}
 
     if rank != 0:
         if world > 1:
@@ -279,9 +310,12 @@ def main():
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": B * N_POINTS * 4 * 4,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+        "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+        "gpu_launches_note": "det3d_b200 kernels per step counted by d3b_launch_count() in an eager pass; the timed "
+                             "region replays the same kernel nodes from a CUDA graph" if use_graph else "counted in an eager pass",
         "clocks": clocks, "roofline": roofline,
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         from det3d_b200.core.anchor.anchor_generator import anchors_for_tasks
         from oracle.second_cpu import SecondCPU

@@ -35,6 +35,7 @@ class InferencePipeline:
         self._anchors = [torch.from_numpy(a).to(self.device) for a in anchors]
         self._anchor_cache = {}
         self.strict_fp32 = strict_fp32
+        self._graphs = {}
 
     def anchors(self, batch):
         a = self._anchor_cache.get(batch)
@@ -61,6 +62,35 @@ class InferencePipeline:
             torch.backends.cudnn.allow_tf32 = prev
         det["voxel_counts"] = vox["counts"]
         return det
+
+    @torch.no_grad()
+    def forward_graphed(self, points, offsets):
+        """forward_device + pack replayed from a CUDA graph (captured on first use per `offsets`).
+
+        Every stage has static shapes and device-resident counts, so the whole forward -- ~50
+        det3d_b200 launches plus the torch glue -- is one graph launch.  `points` may live on the
+        host (pinned) or the device; it is copied into the graph's static input buffer.
+        Returns the packed detections [B, D, nd+3] (a static buffer: consume before the next call)."""
+        key = tuple(int(o) for o in offsets)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_pts = torch.zeros((key[-1], points.shape[1]), dtype=torch.float32, device=self.device)
+            static_pts.copy_(points)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):                      # warm-up: lazy buffers, weight packing, cuDNN plans
+                    self.pack(self.forward_device(static_pts, list(key)))
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.pack(self.forward_device(static_pts, list(key)))
+            entry = self._graphs[key] = (graph, static_pts, out)
+        graph, static_pts, out = entry
+        static_pts.copy_(points, non_blocking=True)
+        graph.replay()
+        return out
 
     @staticmethod
     def pack(det):

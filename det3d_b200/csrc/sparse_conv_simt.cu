@@ -147,9 +147,75 @@ sparse_to_dense_kernel(const float* __restrict__ feat, const int* __restrict__ c
   }
 }
 
+// rows [n, C] -> channels-last BEV rows [B*H*W, C*D] (pre-zeroed), channel = c*D + z.
+__global__ void __launch_bounds__(256)
+sparse_to_bev_rows_kernel(const float* __restrict__ feat, const int* __restrict__ coors,
+                          const int* __restrict__ n_rows, int row_cap, int C, int D, int H, int W, int B,
+                          float* __restrict__ out) {
+  const int n = min(*n_rows, row_cap);
+  const long long total = (long long)n * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / C), c = (int)(e - (long long)r * C);
+    const int4 q = *reinterpret_cast<const int4*>(coors + (size_t)r * 4);
+    if ((unsigned)q.x >= (unsigned)B || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
+        (unsigned)q.w >= (unsigned)W)
+      continue;
+    out[(((size_t)q.x * H + q.z) * W + q.w) * ((size_t)C * D) + (size_t)c * D + q.y] = feat[e];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dense2d_rulebook_kernel(int B, int H, int W, int kh, int kw, int ph, int pw, int* __restrict__ nbr,
+                        unsigned int* __restrict__ tile_mask, int* __restrict__ n_rows) {
+  const int n = B * H * W;
+  const int kvol = kh * kw;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { n_rows[0] = n; n_rows[1] = n; }
+  const long long total = (long long)n * kvol;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e / n), row = (int)(e - (long long)k * n);
+    const int x = row % W, y = (row / W) % H, b = row / (W * H);
+    const int yy = y + k / kw - ph, xx = x + k % kw - pw;
+    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    nbr[e] = ok ? (b * H + yy) * W + xx : -1;
+  }
+  const unsigned int full = kvol >= 32 ? 0xffffffffu : ((1u << kvol) - 1u);
+  const int tiles = (n + kTileM - 1) / kTileM;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < tiles; t += gridDim.x * blockDim.x) tile_mask[t] = full;
+}
+
 }  // namespace d3b
 
 using namespace d3b;
+
+extern "C" int d3b_sparse_to_bev_rows(const float* feat, const int32_t* coors, const int32_t* n_rows,
+                                      int32_t row_cap, int32_t channels, const int32_t spatial[3],
+                                      int32_t batch, float* out_rows, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(feat && coors && n_rows && spatial && out_rows, "d3b_sparse_to_bev_rows: null argument");
+  D3B_REQUIRE(channels >= 1 && batch >= 1 && row_cap >= 0, "d3b_sparse_to_bev_rows: bad shape");
+  if (row_cap == 0) return D3B_OK;
+  sparse_to_bev_rows_kernel<<<grid_for((long long)row_cap * channels, 256), 256, 0, stream>>>(
+      feat, coors, n_rows, row_cap, channels, spatial[0], spatial[1], spatial[2], batch, out_rows);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+extern "C" int d3b_rulebook_dense2d(int32_t batch, int32_t height, int32_t width, const int32_t ksize[2],
+                                    const int32_t padding[2], int32_t* nbr, uint32_t* tile_mask,
+                                    int32_t* n_rows, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(ksize && padding && nbr && tile_mask && n_rows, "d3b_rulebook_dense2d: null argument");
+  D3B_REQUIRE(batch >= 1 && height >= 1 && width >= 1 && ksize[0] >= 1 && ksize[1] >= 1 &&
+                  ksize[0] * ksize[1] <= 32 && (long long)batch * height * width < (1ll << 31),
+              "d3b_rulebook_dense2d: bad shape");
+  const long long total = (long long)batch * height * width * ksize[0] * ksize[1];
+  dense2d_rulebook_kernel<<<grid_for(total, 256), 256, 0, stream>>>(batch, height, width, ksize[0], ksize[1],
+                                                                 padding[0], padding[1], nbr, tile_mask, n_rows);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
 
 extern "C" int d3b_sparse_conv(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask,
                                const int32_t* n_out, int32_t out_cap, const d3b_conv_params* p,

@@ -32,7 +32,9 @@ namespace d3b {
 
 constexpr int kTcTileM = 128;
 constexpr int kTcKc = 32;               // channels per stage = one 128-byte swizzle row
-constexpr int kTcThreads = 160;         // warps 0-3: gather + epilogue, warp 4: TMEM alloc + MMA issue
+constexpr int kTcGroups = 3;            // gather groups of 4 warps, each producing every 3rd pipeline slot
+constexpr int kTcMmaWarp = 4 * kTcGroups;                 // last warp: TMEM alloc + MMA issue
+constexpr int kTcThreads = 128 * kTcGroups + 32;
 constexpr int kABytes = kTcTileM * 128; // one A tile (hi or lo)
 
 // ---- PTX wrappers --------------------------------------------------------------------
@@ -146,14 +148,14 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 128 + 1);  // 128 gather threads + the expect_tx arrive
+      mbar_init(full_bar(s), 128 + 1);  // the 128 gather threads of one group + the expect_tx arrive
       mbar_init(empty_bar(s), 1);       // tcgen05.commit
     }
     mbar_init(accum_full, 1);
-    mbar_init(tmem_empty, 128);
+    mbar_init(tmem_empty, 128 * kTcGroups);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -164,66 +166,98 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  uint32_t it = 0;        // pipeline slot counter (same sequence in producer and MMA roles)
+  uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
   uint32_t tile_it = 0;   // accumulator phase counter
 
-  if (warp < 4) {
-    // ===================== gather producers, then epilogue =====================
+  if (warp < kTcMmaWarp) {
+    // ============ gather producers (kTcGroups groups of 4 warps), then epilogue ============
+    // Group g produces the pipeline slots it with it % kTcGroups == g; inside a tile it keeps the
+    // neighbour indices two slots and the feature rows one slot ahead in registers, so the
+    // dependent nbr -> feature -> shared-memory chain of ~kTcGroups*2 slots is in flight per SM.
+    const int group = warp >> 2, wq = warp & 3;
     const int g = lane >> 3, c = lane & 7;
+    const bool issues_tma = (wq == 0 && lane == 0);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * kTcTileM;
-      unsigned int mask = tile_mask[tile];
-      const bool any = mask != 0;
-      while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int my_row = row0 + warp * 32 + lane;
-        const int my_nbr = my_row < n_out ? nbr[(size_t)k * out_cap + my_row] : -1;
-        for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          uint8_t* stage = smem_gen + (size_t)s * Cfg::kStageBytes;
-          if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
-            tma_bulk_g2s(smem_base + s * Cfg::kStageBytes + 2 * kABytes,
-                         packed + ((size_t)k * n_kb + kb) * (2 * Cfg::kBBytes / 4), 2 * Cfg::kBBytes, full_bar(s));
-          }
-          float4 v[8];
-          const int ch = kb * kTcKc + c * 4;
+      const unsigned int mask = tile_mask[tile];
+      const int n_slots = __popc(mask) * n_kb;
+      const int my_row = row0 + wq * 32 + lane;
+
+      auto slot_k = [&](int j) {            // (j / n_kb)-th set bit of the tile's offset mask
+        unsigned int m = mask;
+        for (int t = j / n_kb; t > 0; --t) m &= m - 1;
+        return __ffs(m) - 1;
+      };
+      auto load_nbr = [&](int j) -> int {
+        return my_row < n_out ? __ldg(nbr + (size_t)slot_k(j) * out_cap + my_row) : -1;
+      };
+      auto load_feat = [&](int j, int my_nbr, float4 (&v)[8]) {
+        const int ch = (j % n_kb) * kTcKc + c * 4;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int src = __shfl_sync(0xffffffffu, my_nbr, 4 * j + g);
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src >= 0 && ch < c_in) v[j] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src * c_in + ch));
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int row = warp * 32 + 4 * j + g;
-            float4 hi, lo;
-            split_tf32(v[j].x, hi.x, lo.x);
-            split_tf32(v[j].y, hi.y, lo.y);
-            split_tf32(v[j].z, hi.z, lo.z);
-            split_tf32(v[j].w, hi.w, lo.w);
-            const uint32_t off = sw128_offset(row, c);
-            *reinterpret_cast<float4*>(stage + off) = hi;
-            *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
-          }
-          fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
-          mbar_arrive(full_bar(s));
+        for (int q = 0; q < 8; ++q) {
+          const int src = __shfl_sync(0xffffffffu, my_nbr, 4 * q + g);
+          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src >= 0 && ch < c_in) v[q] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src * c_in + ch));
         }
+      };
+
+      int j = (int)((group + kTcGroups - (it0 % kTcGroups)) % kTcGroups);   // first slot of this group
+      float4 v_cur[8], v_nxt[8];
+      int nbr_nxt = -1, nbr_nxt2 = -1;
+      if (j < n_slots) {
+        const int n0 = load_nbr(j);
+        if (j + kTcGroups < n_slots) nbr_nxt = load_nbr(j + kTcGroups);
+        load_feat(j, n0, v_cur);
       }
-      // ---- epilogue: TMEM -> registers -> fused BN/bias/residual/ReLU -> global ----
-      const int o = row0 + warp * 32 + lane;
+      for (; j < n_slots; j += kTcGroups) {
+        const bool has1 = j + kTcGroups < n_slots, has2 = j + 2 * kTcGroups < n_slots;
+        if (has2) nbr_nxt2 = load_nbr(j + 2 * kTcGroups);
+        if (has1) load_feat(j + kTcGroups, nbr_nxt, v_nxt);
+
+        const uint32_t it = it0 + (uint32_t)j;
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        uint8_t* stage = smem_gen + (size_t)s * Cfg::kStageBytes;
+        if (issues_tma) {
+          mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
+          tma_bulk_g2s(smem_base + s * Cfg::kStageBytes + 2 * kABytes,
+                       packed + ((size_t)slot_k(j) * n_kb + (j % n_kb)) * (2 * Cfg::kBBytes / 4), 2 * Cfg::kBBytes,
+                       full_bar(s));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int row = wq * 32 + 4 * q + g;
+          float4 hi, lo;
+          split_tf32(v_cur[q].x, hi.x, lo.x);
+          split_tf32(v_cur[q].y, hi.y, lo.y);
+          split_tf32(v_cur[q].z, hi.z, lo.z);
+          split_tf32(v_cur[q].w, hi.w, lo.w);
+          const uint32_t off = sw128_offset(row, c);
+          *reinterpret_cast<float4*>(stage + off) = hi;
+          *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
+        }
+        fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar(s));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v_cur[q] = v_nxt[q];
+        nbr_nxt = nbr_nxt2;
+      }
+      it0 += (uint32_t)n_slots;
+
+      // ---- epilogue: TMEM -> registers -> fused BN/bias/residual/ReLU -> global; the groups
+      //      split the 16-column chunks between them ----
+      const bool any = n_slots != 0;
+      const int o = row0 + wq * 32 + lane;
       if (any) {
         mbar_wait(accum_full, tile_it & 1u);
         tc_fence_after();
       }
 #pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
+      for (int c0 = group * 16; c0 < COUT; c0 += 16 * kTcGroups) {
         uint32_t r[16];
         if (any) {
-          tc_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+          tc_ld16(tmem_d + ((uint32_t)(wq * 32) << 16) + c0, r);
         } else {
 #pragma unroll
           for (int q = 0; q < 16; ++q) r[q] = 0u;
@@ -262,39 +296,38 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
       }
     }
   } else {
-    // ===================== MMA issuer (one elected lane of warp 4) =====================
+    // ===================== MMA issuer (one elected lane of the last warp) =====================
     constexpr uint32_t idesc = umma_idesc_tf32(kTcTileM, COUT);
+    uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      unsigned int mask = tile_mask[tile];
+      const unsigned int mask = tile_mask[tile];
       if (mask == 0) continue;
+      const int n_slots = __popc(mask) * n_kb;
       mbar_wait(tmem_empty, (tile_it & 1u) ^ 1u);
       tc_fence_after();
       uint32_t accumulate = 0;
-      while (mask) {
-        mask &= mask - 1;
-        for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
-            const uint32_t a_lo = a_hi + kABytes;
-            const uint32_t b_hi = a_lo + kABytes;
-            const uint32_t b_lo = b_hi + Cfg::kBBytes;
+      for (int j = 0; j < n_slots; ++j, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_lo + kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-            for (int kk = 0; kk < kTcKc / 8; ++kk) {
-              const uint32_t adv = kk * 32;  // 8 tf32 = 32 bytes along K inside the swizzle row
-              tc_mma_tf32(tmem_d, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, accumulate);
-              tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
-              tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
-              accumulate = 1u;
-            }
-            tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+          for (int kk = 0; kk < kTcKc / 8; ++kk) {
+            const uint32_t adv = kk * 32;  // 8 tf32 = 32 bytes along K inside the swizzle row
+            tc_mma_tf32(tmem_d, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, accumulate);
+            tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
+            tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
+            accumulate = 1u;
           }
-          __syncwarp();
-          accumulate = 1u;
+          tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
         }
+        __syncwarp();
+        accumulate = 1u;
       }
       if (lane == 0) tc_commit(accum_full);
       __syncwarp();
@@ -304,7 +337,7 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kTcMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");

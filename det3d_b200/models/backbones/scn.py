@@ -123,6 +123,17 @@ class _SparseMiddleEncoder(nn.Module):
         n, c, d, h, w = dense.shape
         return dense.view(n, c * d, h, w)
 
+    def forward_rows(self, voxel_features, coors, batch_size, input_shape, n_dev=None):
+        """Channels-last variant: (rows [B*H*W, C*D], (B, H, W)); rows.view(B,H,W,-1).permute(0,3,1,2)
+        equals forward()'s [B, C*D, H, W]."""
+        if self.training:
+            raise RuntimeError("det3d_b200 middle encoders are inference-only: call .eval()")
+        sparse_shape = [int(v) for v in (np.array(input_shape[::-1]) + [1, 0, 0])]
+        fused = self.fused()
+        rows = fused.run(voxel_features, coors.int(), int(batch_size), sparse_shape, n_dev=n_dev, bev_rows=True)
+        _d, h, w = fused._state["final_level"].spatial
+        return rows, (int(batch_size), h, w)
+
     def forward_unfused(self, voxel_features, coors, batch_size, input_shape):
         """Layer-by-layer path through the spconv-style modules (API parity / cross-check)."""
         sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]

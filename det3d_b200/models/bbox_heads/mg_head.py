@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from det3d_b200 import _lib
+from det3d_b200.core.bbox import box_torch_ops
 from det3d_b200.ops.nms import nms_ops
 
 from ..builder import build_loss
@@ -100,12 +101,15 @@ class MultiGroupHead(nn.Module):
         raise NotImplementedError("training is out of scope for det3d_b200 (inference hot path only)")
 
     # ------------------------------------------------------------------ predict
-    def _task_device_detections(self, task_id, test_cfg, cls_preds, reg_preds, dir_preds):
+    def _task_device_detections(self, task_id, test_cfg, cls_preds, box_preds, anchors, dir_preds):
         """One task, whole batch, fixed shapes, no host sync.
 
-        cls_preds [B,A,C] logits, reg_preds [B,A,7|9] decoded boxes, dir_preds [B,A,2] or None.
+        cls_preds [B,A,C] logits, box_preds [B,A,code] encodings, anchors [B,A,nd], dir_preds [B,A,2] | None.
         -> boxes [B,P,nd], scores [B,P], labels [B,P] int64, valid [B,P] bool  (P = nms_post_max_size)
-        """
+
+        Same selection as mg_head.py:995-1025 (score filter, then top-`nms_pre_max_size`), done as
+        top-k first / filter second (sigmoid is monotonic, the passing set is a prefix of the top-k),
+        so only the `pre` selected anchors are decoded instead of all 70,400."""
         nms_cfg = test_cfg["nms"] if isinstance(test_cfg, dict) else test_cfg.nms
         if nms_cfg["use_multi_class_nms"]:
             raise NotImplementedError("use_multi_class_nms=True is not used by the Det3D configs in scope")
@@ -116,29 +120,29 @@ class MultiGroupHead(nn.Module):
         thr = float(test_cfg["score_threshold"])
         pre = min(int(nms_cfg["nms_pre_max_size"]), A)
         post = min(int(nms_cfg["nms_post_max_size"]), pre)
-        total = torch.sigmoid(cls_preds.float())
+        logits = cls_preds.float()
         if C == 1:
-            top_scores = total.squeeze(-1)
-            top_labels = torch.zeros((B, A), dtype=torch.long, device=dev)
+            top_logit, top_labels = logits.squeeze(-1), None
         else:
-            top_scores, top_labels = torch.max(total, dim=-1)
+            top_logit, top_labels = torch.max(logits, dim=-1)
+        sel_logit, sel_idx = torch.topk(top_logit, k=pre, dim=1)                 # descending
+        sel_scores = torch.sigmoid(sel_logit)
         if thr > 0.0:
-            passed = top_scores >= thr
-            ranked = torch.where(passed, top_scores, torch.full_like(top_scores, -1.0))
+            n_valid = (sel_scores >= thr).sum(dim=1).to(torch.int32)
         else:
-            passed = torch.ones_like(top_scores, dtype=torch.bool)
-            ranked = top_scores
-        sel_scores, sel_idx = torch.topk(ranked, k=pre, dim=1)           # descending
-        n_valid = torch.minimum(passed.sum(dim=1), torch.tensor(pre, device=dev)).to(torch.int32)
-        reg = reg_preds.float()
-        nd = reg.shape[-1]
-        cand = torch.gather(reg, 1, sel_idx.unsqueeze(-1).expand(B, pre, nd))    # [B,pre,nd]
-        boxes = torch.zeros((B, post, nd), dtype=torch.float32, device=dev)
-        scores = torch.zeros((B, post), dtype=torch.float32, device=dev)
-        labels = torch.zeros((B, post), dtype=torch.long, device=dev)
-        valid = torch.zeros((B, post), dtype=torch.bool, device=dev)
+            n_valid = torch.full((B,), pre, dtype=torch.int32, device=dev)
+        nd = anchors.shape[-1]
+        code = box_preds.shape[-1]
+        enc = torch.gather(box_preds.float(), 1, sel_idx.unsqueeze(-1).expand(B, pre, code))
+        anc = torch.gather(anchors.float(), 1, sel_idx.unsqueeze(-1).expand(B, pre, nd))
+        cand = self.box_coder.decode_torch(enc[:, :, : self.box_coder.code_size], anc)   # [B,pre,nd]
+        if self.use_direction_classifier and dir_preds is not None:
+            dsel = torch.gather(dir_preds, 1, sel_idx.unsqueeze(-1).expand(B, pre, 2))
+            dir_labels = torch.max(dsel, dim=-1)[1]
+        lab = torch.zeros((B, pre), dtype=torch.long, device=dev) if top_labels is None else torch.gather(top_labels, 1, sel_idx)
         use_rot = bool(nms_cfg["use_rotate_nms"])
         slot = torch.arange(post, device=dev)
+        keep_all, ok_all = [], []
         for b in range(B):
             if use_rot:
                 nms_boxes = cand[b][:, [0, 1, 3, 4, nd - 1]].contiguous()
@@ -146,29 +150,31 @@ class MultiGroupHead(nn.Module):
                                                           float(nms_cfg["nms_iou_threshold"]), post,
                                                           n_dev=n_valid[b:b + 1])
             else:
-                s, c = torch.sin(cand[b][:, nd - 1]), torch.cos(cand[b][:, nd - 1])
-                hw = 0.5 * (cand[b][:, 3] * c.abs() + cand[b][:, 4] * s.abs())
-                hl = 0.5 * (cand[b][:, 3] * s.abs() + cand[b][:, 4] * c.abs())
-                bb = torch.stack([cand[b][:, 0] - hw, cand[b][:, 1] - hl, cand[b][:, 0] + hw, cand[b][:, 1] + hl,
-                                  torch.zeros_like(hw)], dim=1).contiguous()
+                corners = box_torch_ops.center_to_corner_box2d(cand[b][:, :2], cand[b][:, 3:5], cand[b][:, nd - 1])
+                bb = torch.cat([box_torch_ops.corner_to_standup_nd(corners),
+                                torch.zeros((pre, 1), device=dev)], dim=1).contiguous()
                 keep_idx, keep_count = nms_ops.nms_sorted(bb, _lib.BOX_XYXYR, float(nms_cfg["nms_iou_threshold"]),
                                                           post, n_dev=n_valid[b:b + 1], axis_aligned=True)
             ok = slot < keep_count.to(torch.long)
-            kidx = torch.where(ok, keep_idx[:post], torch.zeros_like(keep_idx[:post]))
-            src = sel_idx[b][kidx]
-            bx = cand[b][kidx]
-            if self.use_direction_classifier and dir_preds is not None:
-                dir_labels = torch.max(dir_preds[b], dim=-1)[1][src]
-                opp = ((bx[:, -1] - self.direction_offset) > 0) ^ dir_labels.bool()
-                bx = torch.cat([bx[:, :-1], (bx[:, -1] + torch.where(opp, np.pi, 0.0).to(bx.dtype)).unsqueeze(-1)], 1)
-            boxes[b] = bx
-            scores[b] = sel_scores[b][kidx]
-            labels[b] = top_labels[b][src]
-            valid[b] = ok
+            keep_all.append(torch.where(ok, keep_idx[:post], torch.zeros_like(keep_idx[:post])))
+            ok_all.append(ok)
+        kidx = torch.stack(keep_all)                                              # [B,post]
+        valid = torch.stack(ok_all)
+        boxes = torch.gather(cand, 1, kidx.unsqueeze(-1).expand(B, post, nd))
+        scores = torch.gather(sel_scores, 1, kidx)
+        labels = torch.gather(lab, 1, kidx)
+        if self.use_direction_classifier and dir_preds is not None:
+            dl = torch.gather(dir_labels, 1, kidx)
+            opp = ((boxes[..., -1] - self.direction_offset) > 0) ^ dl.bool()
+            boxes = torch.cat([boxes[..., :-1], (boxes[..., -1] + opp.to(boxes.dtype) * np.pi).unsqueeze(-1)], -1)
         rng = test_cfg["post_center_limit_range"]
         if rng is not None and len(rng) > 0:
-            r = torch.tensor(list(rng), dtype=torch.float32, device=dev)
-            valid &= (boxes[..., :3] >= r[:3]).all(-1) & (boxes[..., :3] <= r[3:]).all(-1)
+            key = (tuple(float(v) for v in rng), dev)
+            cache = self.__dict__.setdefault("_range_cache", {})
+            r = cache.get(key)
+            if r is None:   # built once (a host->device copy is not CUDA-graph capturable)
+                r = cache[key] = torch.tensor(list(rng), dtype=torch.float32, device=dev)
+            valid = valid & (boxes[..., :3] >= r[:3]).all(-1) & (boxes[..., :3] <= r[3:]).all(-1)
         return boxes, scores, labels, valid
 
     def predict_device(self, example, preds_dicts, test_cfg):
@@ -183,12 +189,11 @@ class MultiGroupHead(nn.Module):
             B = anchors.shape[0]
             anchors = anchors.view(B, -1, self.anchor_dim)
             code = self.box_n_dim - 2 if self.bev_only else self.box_n_dim
-            box_preds = preds["box_preds"].view(B, -1, code)
+            box_preds = preds["box_preds"].reshape(B, -1, code)
             n_cls = self.num_classes[task_id] if self.encode_background_as_zeros else self.num_classes[task_id] + 1
-            cls_preds = preds["cls_preds"].view(B, -1, n_cls)
-            reg = self.box_coder.decode_torch(box_preds[:, :, : self.box_coder.code_size], anchors)
-            dirs = preds["dir_cls_preds"].view(B, -1, 2) if self.use_direction_classifier else None
-            bx, sc, lb, ok = self._task_device_detections(task_id, test_cfg, cls_preds, reg, dirs)
+            cls_preds = preds["cls_preds"].reshape(B, -1, n_cls)
+            dirs = preds["dir_cls_preds"].reshape(B, -1, 2) if self.use_direction_classifier else None
+            bx, sc, lb, ok = self._task_device_detections(task_id, test_cfg, cls_preds, box_preds, anchors, dirs)
             outs.append((bx, sc, lb + flag, ok))
             flag += self.num_classes[task_id]
         return dict(boxes=torch.cat([o[0] for o in outs], 1), scores=torch.cat([o[1] for o in outs], 1),

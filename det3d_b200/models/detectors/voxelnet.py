@@ -32,6 +32,19 @@ class SingleStageDetector(nn.Module):
 
 @DETECTORS.register_module
 class VoxelNet(SingleStageDetector):
+    #: route the dense RPN + heads through the channels-last tensor-core path when its shape allows
+    use_fused_bev = True
+    _bev = None
+
+    def fused_bev(self):
+        """FusedBevStack for (neck, bbox_head) when the RPN is the stride-1 SECOND shape, else None."""
+        if self._bev is None:
+            from det3d_b200.ops.spconv.bev import FusedBevStack, rpn_is_fusable
+            ok = (self.with_neck and hasattr(self.backbone, "forward_rows") and rpn_is_fusable(self.neck)
+                  and not self.training)
+            self._bev = FusedBevStack(self.neck, self.bbox_head) if ok else False
+        return self._bev or None
+
     def extract_feat(self, data):
         feats = self.reader(data["features"], data["num_voxels"])
         x = self.backbone(feats, data["coors"], data["batch_size"], data["input_shape"],
@@ -43,7 +56,14 @@ class VoxelNet(SingleStageDetector):
         data = dict(features=example["voxels"], num_voxels=example["num_points"],
                     coors=example["coordinates"], batch_size=len(num_voxels),
                     input_shape=example["shape"][0], n_dev=example.get("n_voxels_dev"))
-        preds = self.bbox_head(self.extract_feat(data))
+        bev = self.fused_bev() if (self.use_fused_bev and not return_loss) else None
+        if bev is not None:
+            feats = self.reader(data["features"], data["num_voxels"])
+            rows, (b, h, w) = self.backbone.forward_rows(feats, data["coors"], data["batch_size"],
+                                                          data["input_shape"], n_dev=data["n_dev"])
+            preds = bev.run(rows, b, h, w)
+        else:
+            preds = self.bbox_head(self.extract_feat(data))
         if return_loss:
             return self.bbox_head.loss(example, preds)
         if kwargs.get("device_output", False):

@@ -288,6 +288,17 @@ def sparse_to_dense(feat, level, out=None):
     return out
 
 
+def sparse_to_bev_rows(feat, level, out):
+    """rows -> channels-last BEV rows [B*H*W, C*D] (channel = c*D + z); `out` must be zero-filled."""
+    c = feat.shape[1]
+    st = _lib.lib().d3b_sparse_to_bev_rows(
+        feat.data_ptr(), level.coors.data_ptr(), level.n.data_ptr(), level.cap, c, _i3(level.spatial),
+        level.batch, out.data_ptr(), _lib.current_stream(),
+    )
+    _lib.check(st, "d3b_sparse_to_bev_rows")
+    return out
+
+
 def level_from_coors(coors, spatial, batch, n_dev=None):
     """Level 0 from caller coordinates ([M,4] int32 b,z,y,x) + hash index."""
     coors = coors.to(torch.int32).contiguous()

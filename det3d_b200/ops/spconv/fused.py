@@ -146,7 +146,7 @@ class FusedSparseEncoder:
         return t
 
     # ---- run ------------------------------------------------------------------------
-    def run(self, features, coors, batch_size, spatial, n_dev=None, row_cap=None):
+    def run(self, features, coors, batch_size, spatial, n_dev=None, row_cap=None, bev_rows=False):
         """features [M, C] f32, coors [M, 4] int (b,z,y,x) -> dense [B, C_out, D, H, W].
 
         With `n_dev` (int32[>=1] device tensor) only the first n_dev[0] rows are
@@ -187,6 +187,15 @@ class FusedSparseEncoder:
             if L.residual:
                 identity = None
             x = out
+        if bev_rows:
+            # channels-last [B*H*W, C*D] with channel = c*D + z: same values as dense.view(B, C*D, H, W)
+            d, h, w = st["final_level"].spatial
+            rows = st.get("bev_rows")
+            if rows is None:
+                rows = st["bev_rows"] = torch.empty((batch_size * h * w, x.shape[1] * d), dtype=torch.float32, device=device)
+            rows.zero_()
+            core.sparse_to_bev_rows(x, st["final_level"], rows)
+            return rows
         dense = st["dense"]
         dense.zero_()
         core.sparse_to_dense(x, st["final_level"], out=dense)

@@ -157,6 +157,20 @@ int d3b_sparse_to_dense(const float* feat, const int32_t* coors, const int32_t* 
                         int32_t row_cap, int32_t channels, const int32_t spatial[3],
                         int32_t batch, float* out, void* stream);
 
+/* rows -> zero-initialised channels-last BEV rows [B*H*W, C*D], channel = c*D + z: the same
+ * values as .dense().view(B, C*D, H, W) (scn.py:192-195), laid out for the NHWC dense path. */
+int d3b_sparse_to_bev_rows(const float* feat, const int32_t* coors, const int32_t* n_rows,
+                           int32_t row_cap, int32_t channels, const int32_t spatial[3],
+                           int32_t batch, float* out_rows, void* stream);
+
+/* Static rulebook of a dense stride-1 2-D convolution over a [B, H, W] grid (row = (b*H+y)*W+x):
+ * nbr[k*n + row] = row of (y + ky - pad_y, x + kx - pad_x) or -1; k = ky*kw + kx.  Lets the
+ * dense RPN (det3d/models/necks/rpn.py:124-159) and head 1x1 convs (mg_head.py:198-230) run
+ * through d3b_sparse_conv in channels-last layout.  n = B*H*W is also written to n_rows[0..1]. */
+int d3b_rulebook_dense2d(int32_t batch, int32_t height, int32_t width, const int32_t ksize[2],
+                         const int32_t padding[2], int32_t* nbr, uint32_t* tile_mask,
+                         int32_t* n_rows, void* stream);
+
 /* ========================================================================= *
  * 4. Rotated-box BEV IoU / NMS
  * ========================================================================= */

@@ -105,3 +105,29 @@ def test_model_predict_api(setup):
     ref = pipe.unpack(pipe.infer_host([torch.from_numpy(pts)]))[0]
     assert out[0]["box3d_lidar"].shape[0] == ref["box3d_lidar"].shape[0]
     assert torch.allclose(out[0]["box3d_lidar"].cpu(), ref["box3d_lidar"], atol=1e-4)
+
+
+def test_fused_bev_path_matches_cudnn_path(setup):
+    """RPN + heads through the channels-last tcgen05 kernels vs the module's torch/cuDNN fp32 forward."""
+    from det3d_b200.utils.synthetic import lidar_like_cloud
+    cfg, pipe, cpu = setup
+    model = pipe.model
+    assert model.fused_bev() is not None
+    pts = torch.from_numpy(lidar_like_cloud(20000, cfg.voxel_generator.range, 4, 5)).cuda()
+    vox = pipe.voxelizer(pts, [0, 20000])
+    grid = [int(g) for g in pipe.grid_size]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            rows, (b, h, w) = model.backbone.forward_rows(vox["mean"], vox["coors"], 1, grid, n_dev=vox["counts"][1:2])
+            dense = model.backbone(vox["mean"], vox["coors"], 1, grid, n_dev=vox["counts"][1:2])
+            assert torch.equal(rows.view(b, h, w, -1).permute(0, 3, 1, 2), dense)
+            fused = model.fused_bev().run(rows, b, h, w)
+            ref = model.bbox_head(model.neck(dense))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    for key in ("box_preds", "cls_preds", "dir_cls_preds"):
+        a, r = fused[0][key], ref[0][key]
+        assert a.shape == r.shape
+        assert float((a - r).abs().max()) <= 2e-4, key
