@@ -226,10 +226,10 @@ rb_scan_sums(int* block_sums, int n_blocks, int out_cap, int* n_out) {
   }
 }
 
+// prefix pass: word_prefix[w] = number of set bits before word w (block offsets already scanned)
 __global__ void __launch_bounds__(kScanThreads)
-rb_scan_emit(const unsigned int* __restrict__ bitmap, long long n_words,
-             const int* __restrict__ block_offsets, SiteIndexDev out, int out_cap,
-             int* __restrict__ word_prefix, int* __restrict__ out_coors) {
+rb_scan_prefix(const unsigned int* __restrict__ bitmap, long long n_words,
+               const int* __restrict__ block_offsets, int* __restrict__ word_prefix) {
   __shared__ int smem[32];
   const long long base = (long long)blockIdx.x * kScanWordsPerBlock + threadIdx.x * kScanWordsPerThread;
   unsigned int w[kScanWordsPerThread];
@@ -245,26 +245,39 @@ rb_scan_emit(const unsigned int* __restrict__ bitmap, long long n_words,
   for (int j = 0; j < kScanWordsPerThread; ++j) {
     if (base + j >= n_words) break;
     word_prefix[base + j] = rank;
-    unsigned int bits = w[j];
-    if (bits == 0u) continue;
-    // decompose the word's first cell once (64-bit divisions), then walk bits with carries
-    unsigned long long lin = (unsigned long long)(base + j) << 5;
-    const int x0 = (int)(lin % out.W); lin /= out.W;
-    const int y0 = (int)(lin % out.H); lin /= out.H;
-    const int z0 = (int)(lin % out.D);
-    const int b0 = (int)(lin / out.D);
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if (rank < out_cap) {
-        int x = x0 + b, y = y0, z = z0, bb = b0;
-        while (x >= out.W) {
-          x -= out.W;
-          if (++y >= out.H) { y = 0; if (++z >= out.D) { z = 0; ++bb; } }
+    rank += __popc(w[j]);
+  }
+}
+
+// emit pass: one warp per bitmap word, lane = bit -> coordinates of every set bit at its rank.
+// (A thread-per-word loop serialises up to 128 stores in dense regions; this does not.)
+__global__ void __launch_bounds__(256)
+rb_emit_coors(const unsigned int* __restrict__ bitmap, const int* __restrict__ word_prefix, long long n_words,
+              SiteIndexDev out, int out_cap, int* __restrict__ out_coors) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  // each warp scans 32 words at a time: lane l tests word (chunk*32 + l), then the warp expands the non-zero ones
+  for (long long chunk = warp0; chunk * 32 < n_words; chunk += n_warps) {
+    const long long wi = chunk * 32 + lane;
+    const unsigned int mine = wi < n_words ? bitmap[wi] : 0u;
+    unsigned int nz = __ballot_sync(0xffffffffu, mine != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const unsigned int bits = __shfl_sync(0xffffffffu, mine, src);
+      const long long w = chunk * 32 + src;
+      if ((bits >> lane) & 1u) {
+        const int rank = word_prefix[w] + __popc(bits & ((1u << lane) - 1u));
+        if (rank < out_cap) {
+          unsigned long long lin = ((unsigned long long)w << 5) + lane;
+          const int x = (int)(lin % out.W); lin /= out.W;
+          const int y = (int)(lin % out.H); lin /= out.H;
+          const int z = (int)(lin % out.D);
+          const int bb = (int)(lin / out.D);
+          *reinterpret_cast<int4*>(out_coors + (size_t)rank * 4) = make_int4(bb, z, y, x);
         }
-        *reinterpret_cast<int4*>(out_coors + (size_t)rank * 4) = make_int4(bb, z, y, x);
       }
-      ++rank;
     }
   }
 }
@@ -366,8 +379,11 @@ extern "C" int d3b_rulebook_conv(const int32_t* in_coors, const int32_t* n_in, i
   D3B_LAUNCH_CHECK();
   rb_scan_sums<<<1, kScanThreads, 0, stream>>>(block_sums, n_blocks, out_cap, n_out);
   D3B_LAUNCH_CHECK();
-  rb_scan_emit<<<n_blocks, kScanThreads, 0, stream>>>(out_index->bitmap, n_words, block_sums, out,
-                                                      out_cap, out_index->word_prefix, out_coors);
+  rb_scan_prefix<<<n_blocks, kScanThreads, 0, stream>>>(out_index->bitmap, n_words, block_sums,
+                                                        out_index->word_prefix);
+  D3B_LAUNCH_CHECK();
+  rb_emit_coors<<<grid_for(n_words, 256), 256, 0, stream>>>(out_index->bitmap, out_index->word_prefix, n_words, out,
+                                                           out_cap, out_coors);
   D3B_LAUNCH_CHECK();
   rb_neighbours<<<grid_for((long long)out_cap * g.kvol, 256), 256, 0, stream>>>(
       out_coors, n_out, out_cap, to_dev(in_index, in_cap), g, nbr, tile_mask);

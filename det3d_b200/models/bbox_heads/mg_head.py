@@ -145,7 +145,8 @@ class MultiGroupHead(nn.Module):
         keep_all, ok_all = [], []
         for b in range(B):
             if use_rot:
-                nms_boxes = cand[b][:, [0, 1, 3, 4, nd - 1]].contiguous()
+                cb = cand[b]   # (no list indexing: it would stage an index tensor through the host)
+                nms_boxes = torch.stack([cb[:, 0], cb[:, 1], cb[:, 3], cb[:, 4], cb[:, nd - 1]], dim=1)
                 keep_idx, keep_count = nms_ops.nms_sorted(nms_boxes, _lib.BOX_XYWLR,
                                                           float(nms_cfg["nms_iou_threshold"]), post,
                                                           n_dev=n_valid[b:b + 1])
