@@ -6,10 +6,10 @@
 // per offset gather -> torch.mm -> scatter-add; call sites
 // det3d/models/backbones/scn.py:106-157).  Here one CTA owns 128 output rows; for
 // every kernel offset that has a neighbour in the tile (tile_mask) and every 32-channel
-// slice of C_in, four producer warps gather the 128 input rows straight from global/L2
-// into a K-major, 128B-swizzled shared-memory tile, and one thread issues
-// tcgen05.mma.kind::tf32 (M=128, N=C_out, K=8) accumulating in TMEM.  No scatter, no
-// atomics; BN/bias/residual/ReLU are applied on the way out of TMEM.
+// slice of C_in ("slot"), a group of four producer warps gathers the 128 input rows
+// straight from global/L2 into a K-major, 128B-swizzled shared-memory tile, and one
+// thread issues tcgen05.mma.kind::tf32 (M=128, N=C_out, K=8) accumulating in TMEM.
+// No scatter, no atomics; BN/bias/residual/ReLU are applied on the way out of TMEM.
 //
 // fp32-equivalent accuracy ("3xTF32"): every fp32 operand x is split exactly into
 //   hi = x with the low 13 mantissa bits cleared (a TF32 number), lo = x - hi (13 bits),
@@ -17,15 +17,24 @@
 // lo.lo term is O(2^-22) relative.  Activations are split in registers while being
 // gathered; weights are split once at load time by d3b_conv_pack_weight, which also
 // lays them out as the exact shared-memory image (K-major, 128B swizzle) so that one
-// cp.async.bulk (TMA) per stage brings the B operand in.
+// cp.async.bulk (TMA) per slot brings the B operand in.
 //
 // Pipeline: NSTAGE-deep ring of {A_hi, A_lo, B_hi, B_lo} tiles guarded by full/empty
 // mbarriers; producers -> (generic-proxy stores + fence.proxy.async + arrive),
-// TMA -> complete_tx, MMA thread -> tcgen05.commit on the empty barrier.  Persistent
-// grid (<= one CTA per SM), tile loop with an accumulator full/empty barrier pair.
+// TMA -> complete_tx, MMA thread -> tcgen05.commit on the empty barrier.  Three producer
+// groups take every third slot so three global round trips are in flight per SM (a thread
+// cannot keep loads in flight across fence.proxy.async -- measured: the fence waits for them);
+// the tile's neighbour indices are staged in shared memory once per tile.  Persistent grid
+// (<= one CTA per SM), tile loop with an accumulator full/empty barrier pair; the groups split
+// the epilogue's 16-column chunks.
+//
+// Measured bound (ncu, profiles/r1_spconv_tc_v3_ncu.md): the L1/shared-memory data pipe --
+// per slot the tensor core re-reads A_hi and B_hi (3 MMAs x 2 operands), the producers store
+// 32 KB and the TMA 2*C_out*128 B; tensor pipe 50 % active on the dense 128->128 layers,
+// 26 % on the sparse 64->64 layers where ~2/3 of the gathered rows are padding.
 //
 // Algorithmic bytes per layer: N_in*C_in*4 + N_out*C_out*4 + P*8 + K*C_in*C_out*4
-// (SURVEY 8d); tensor work issued: 3 * 2 * 128 * C_out * 32 flop per (tile, offset, slice).
+// (SURVEY 8d); tensor work issued: 3 * 2 * 128 * C_out * 32 flop per slot.
 #include "common.cuh"
 
 namespace d3b {
@@ -121,7 +130,8 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = (COUT >= 128) ? 3 : 4;
   static constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers, offsets*/ +
+                                    32 * kTcTileM * 4 /*neighbour rows of the tile*/;
 };
 
 template <int COUT>
@@ -141,6 +151,8 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
   const uint32_t accum_full = bar_base + 8u * (2 * Cfg::kStages);
   const uint32_t tmem_empty = bar_base + 8u * (2 * Cfg::kStages + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 2));
+  int* koff_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 128);          // [32] active offsets
+  int* nbr_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);           // [32][128] neighbour rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = min(*n_out_p, out_cap);
@@ -171,49 +183,43 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
 
   if (warp < kTcMmaWarp) {
     // ============ gather producers (kTcGroups groups of 4 warps), then epilogue ============
-    // Group g produces the pipeline slots it with it % kTcGroups == g; inside a tile it keeps the
-    // neighbour indices two slots and the feature rows one slot ahead in registers, so the
-    // dependent nbr -> feature -> shared-memory chain of ~kTcGroups*2 slots is in flight per SM.
+    // Group g produces the pipeline slots it with it % kTcGroups == g, so kTcGroups dependent
+    // "feature rows -> shared memory" chains are in flight per SM.  A thread must not hold
+    // outstanding global loads across fence.proxy.async (the fence waits for them), hence no
+    // register prefetch: latency is hidden across groups, and the tile's neighbour indices are
+    // staged in shared memory once per tile so a slot costs one global round trip, not two.
     const int group = warp >> 2, wq = warp & 3;
     const int g = lane >> 3, c = lane & 7;
     const bool issues_tma = (wq == 0 && lane == 0);
+    const int ptid = threadIdx.x;  // 0 .. 128*kTcGroups-1 (producer threads come first)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * kTcTileM;
       const unsigned int mask = tile_mask[tile];
-      const int n_slots = __popc(mask) * n_kb;
-      const int my_row = row0 + wq * 32 + lane;
+      const int n_off = __popc(mask);
+      const int n_slots = n_off * n_kb;
 
-      auto slot_k = [&](int j) {            // (j / n_kb)-th set bit of the tile's offset mask
+      // ---- stage nbr[k][row0 .. row0+127] for the active offsets (one global round trip) ----
+      asm volatile("bar.sync 1, %0;" ::"r"(128 * kTcGroups) : "memory");   // previous tile's readers are done
+      for (int idx = ptid; idx < n_off * kTcTileM; idx += 128 * kTcGroups) {
+        const int n = idx >> 7, r = idx & 127;
         unsigned int m = mask;
-        for (int t = j / n_kb; t > 0; --t) m &= m - 1;
-        return __ffs(m) - 1;
-      };
-      auto load_nbr = [&](int j) -> int {
-        return my_row < n_out ? __ldg(nbr + (size_t)slot_k(j) * out_cap + my_row) : -1;
-      };
-      auto load_feat = [&](int j, int my_nbr, float4 (&v)[8]) {
-        const int ch = (j % n_kb) * kTcKc + c * 4;
+        for (int t = n; t > 0; --t) m &= m - 1;
+        const int k = __ffs(m) - 1;
+        if (r == 0) koff_s[n] = k;
+        nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)k * out_cap + row0 + r) : -1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(128 * kTcGroups) : "memory");
+
+      for (int j = (int)((group + kTcGroups - (it0 % kTcGroups)) % kTcGroups); j < n_slots; j += kTcGroups) {
+        const int n = j / n_kb, kb = j - n * n_kb;
+        const int ch = kb * kTcKc + c * 4;
+        float4 v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int src = __shfl_sync(0xffffffffu, my_nbr, 4 * q + g);
+          const int src = nbr_s[n * kTcTileM + wq * 32 + 4 * q + g];
           v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (src >= 0 && ch < c_in) v[q] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src * c_in + ch));
         }
-      };
-
-      int j = (int)((group + kTcGroups - (it0 % kTcGroups)) % kTcGroups);   // first slot of this group
-      float4 v_cur[8], v_nxt[8];
-      int nbr_nxt = -1, nbr_nxt2 = -1;
-      if (j < n_slots) {
-        const int n0 = load_nbr(j);
-        if (j + kTcGroups < n_slots) nbr_nxt = load_nbr(j + kTcGroups);
-        load_feat(j, n0, v_cur);
-      }
-      for (; j < n_slots; j += kTcGroups) {
-        const bool has1 = j + kTcGroups < n_slots, has2 = j + 2 * kTcGroups < n_slots;
-        if (has2) nbr_nxt2 = load_nbr(j + 2 * kTcGroups);
-        if (has1) load_feat(j + kTcGroups, nbr_nxt, v_nxt);
-
         const uint32_t it = it0 + (uint32_t)j;
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
@@ -222,26 +228,23 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
         if (issues_tma) {
           mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
           tma_bulk_g2s(smem_base + s * Cfg::kStageBytes + 2 * kABytes,
-                       packed + ((size_t)slot_k(j) * n_kb + (j % n_kb)) * (2 * Cfg::kBBytes / 4), 2 * Cfg::kBBytes,
+                       packed + ((size_t)koff_s[n] * n_kb + kb) * (2 * Cfg::kBBytes / 4), 2 * Cfg::kBBytes,
                        full_bar(s));
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int row = wq * 32 + 4 * q + g;
           float4 hi, lo;
-          split_tf32(v_cur[q].x, hi.x, lo.x);
-          split_tf32(v_cur[q].y, hi.y, lo.y);
-          split_tf32(v_cur[q].z, hi.z, lo.z);
-          split_tf32(v_cur[q].w, hi.w, lo.w);
+          split_tf32(v[q].x, hi.x, lo.x);
+          split_tf32(v[q].y, hi.y, lo.y);
+          split_tf32(v[q].z, hi.z, lo.z);
+          split_tf32(v[q].w, hi.w, lo.w);
           const uint32_t off = sw128_offset(row, c);
           *reinterpret_cast<float4*>(stage + off) = hi;
           *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
         }
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(s));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v_cur[q] = v_nxt[q];
-        nbr_nxt = nbr_nxt2;
       }
       it0 += (uint32_t)n_slots;
 
