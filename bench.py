@@ -49,18 +49,13 @@ def make_clouds(dist, count, seed0, pcr):
 
 
 def build_model(cfg):
+    """Random-init weights of the named architecture (no checkpoints offline), calibrated so that the
+    detection head sees a realistic workload: ~2k anchors above the score threshold, top-1000 into NMS."""
     import torch
     from det3d.models import build_detector
-    from det3d_b200.utils.synthetic import randomize_bn_
+    from det3d_b200.utils.synthetic import demo_weights_
     torch.manual_seed(0)
-    model = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval()
-    randomize_bn_(model, 0)
-    with torch.no_grad():   # random-init weights of the named architecture; spread scores so NMS sees real work
-        head = model.bbox_head.tasks[0]
-        head.conv_cls.weight.mul_(4.0)
-        head.conv_cls.bias.fill_(-2.5)
-        head.conv_box.weight.mul_(0.3)
-    return model
+    return demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 0)
 
 
 class ClockSampler:

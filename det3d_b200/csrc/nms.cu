@@ -325,60 +325,79 @@ pair_matrix_kernel(int na, const float* __restrict__ boxes_a, int nb, const floa
   out[(size_t)a * nb + b] = MODE == 0 ? iou_xyxyr(pa, pb) : overlap_xyxyr(pa, pb);
 }
 
-// Suppression bitmask, upper triangle only.  blockIdx.x enumerates (row, col)
-// 64-box block pairs with col >= row; thread t owns row box row*64+t.
+// Suppression bitmask, upper triangle only.  A work item is (64-box row block, 64-box column
+// block, 16-row slice) with col >= row; the CTA is 64 (column) x 4 threads, every thread tests 4
+// pairs and a warp ballot assembles 32 mask bits at a time -- 16x more threads in flight per mask
+// word than one-thread-per-row, which is what the ~2k-instruction polygon routine needs at the
+// real operating point (N = 1000: 2176 CTAs instead of 136).
+constexpr int kNmsRowsPerCta = 16;
+constexpr int kNmsSlices = kNmsBlock / kNmsRowsPerCta;
+
 template <int FMT>  // 0 xyxyr rotated, 1 xywlr rotated, 2 axis-aligned (xyxyr boxes, angle ignored)
-__global__ void __launch_bounds__(kNmsBlock)
+__global__ void __launch_bounds__(256)
 nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restrict__ n_dev, float thresh,
                 int col_blocks, unsigned long long* __restrict__ mask) {
   const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int nb = (n + kNmsBlock - 1) / kNmsBlock;
-  // decode linear block id -> (row, col), col >= row, over the nb x nb triangle
   const long long tri = (long long)nb * (nb + 1) / 2;
-  __shared__ float sbox[kNmsBlock * 5];
-  __shared__ Disc sdisc[kNmsBlock];
-  __shared__ Quad squad[FMT == 1 ? kNmsBlock : 1];
-  for (long long bid = blockIdx.x; bid < tri; bid += gridDim.x) {
-    // row r has (nb - r) blocks; find r by solving the triangular number
-    long long rem = bid;
+  const long long items = tri * kNmsSlices;
+  __shared__ float scol[kNmsBlock * 5];
+  __shared__ float srow[kNmsRowsPerCta * 5];
+  __shared__ Disc dcol[FMT == 0 ? kNmsBlock : 1];
+  __shared__ Quad qcol[FMT == 1 ? kNmsBlock : 1];
+  __shared__ Quad qrow[FMT == 1 ? kNmsRowsPerCta : 1];
+  const int tx = threadIdx.x & 63;        // column inside the block
+  const int ty = threadIdx.x >> 6;        // 0..3
+  unsigned int* mask32 = reinterpret_cast<unsigned int*>(mask);
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long bid = item / kNmsSlices;
+    const int slice = (int)(item - bid * kNmsSlices);
+    // linear id over the nb x nb upper triangle -> (row, col): row r owns (nb - r) blocks
     int row = (int)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)bid)) * 0.5);
     if (row < 0) row = 0;
     while ((long long)row * nb - (long long)row * (row - 1) / 2 > bid) --row;
     while ((long long)(row + 1) * nb - (long long)(row + 1) * row / 2 <= bid) ++row;
-    rem = bid - ((long long)row * nb - (long long)row * (row - 1) / 2);
-    const int col = row + (int)rem;
-    const int row_size = min(n - row * kNmsBlock, kNmsBlock);
+    const int col = row + (int)(bid - ((long long)row * nb - (long long)row * (row - 1) / 2));
+    const int row_first = row * kNmsBlock + slice * kNmsRowsPerCta;
     const int col_size = min(n - col * kNmsBlock, kNmsBlock);
     __syncthreads();
+    if (row_first >= n) continue;          // uniform for the CTA
     if ((int)threadIdx.x < col_size) {
       const float* src = boxes + (size_t)(kNmsBlock * col + threadIdx.x) * 5;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) sbox[threadIdx.x * 5 + k] = src[k];
-      if (FMT == 0) sdisc[threadIdx.x] = disc_of_xyxyr(src);
-      if (FMT == 1) squad[threadIdx.x] = quad_of_xywlr(src);
+      for (int k = 0; k < 5; ++k) scol[threadIdx.x * 5 + k] = src[k];
+      if (FMT == 0) dcol[threadIdx.x] = disc_of_xyxyr(src);
+      if (FMT == 1) qcol[threadIdx.x] = quad_of_xywlr(src);
+    }
+    if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + kNmsRowsPerCta && row_first + (int)threadIdx.x - 64 < n) {
+      const int r = threadIdx.x - 64;
+      const float* src = boxes + (size_t)(row_first + r) * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) srow[r * 5 + k] = src[k];
+      if (FMT == 1) qrow[r] = quad_of_xywlr(src);
     }
     __syncthreads();
-    if ((int)threadIdx.x < row_size) {
-      const int cur = kNmsBlock * row + threadIdx.x;
-      const float* cur_box = boxes + (size_t)cur * 5;
-      unsigned long long t = 0;
-      const int start = (row == col) ? threadIdx.x + 1 : 0;
-      if (FMT == 0) {
-        const Disc dc = disc_of_xyxyr(cur_box);
-        const bool prune = thresh >= 0.0f;
-        for (int i = start; i < col_size; i++) {
-          if (prune && surely_disjoint(dc, sdisc[i])) continue;
-          if (iou_xyxyr(cur_box, sbox + i * 5) > thresh) t |= 1ULL << i;
+#pragma unroll 1
+    for (int rr = ty; rr < kNmsRowsPerCta; rr += 4) {
+      const int cur = row_first + rr;      // warp-uniform
+      if (cur >= n) break;
+      bool bit = false;
+      // diagonal block: only columns after the row itself (iou3d_kernel.cu:277-280)
+      const bool active = tx < col_size && (row != col || tx > slice * kNmsRowsPerCta + rr);
+      if (active) {
+        const float* cur_box = srow + rr * 5;
+        if (FMT == 0) {
+          const Disc dc = disc_of_xyxyr(cur_box);
+          if (!(thresh >= 0.0f && surely_disjoint(dc, dcol[tx]))) bit = iou_xyxyr(cur_box, scol + tx * 5) > thresh;
+        } else if (FMT == 1) {
+          bit = suppresses_xywlr(qrow[rr], qcol[tx], thresh, nullptr);
+        } else {
+          bit = iou_axis_aligned(cur_box, scol + tx * 5) > thresh;
         }
-      } else if (FMT == 1) {
-        const Quad qa = quad_of_xywlr(cur_box);
-        for (int i = start; i < col_size; i++)
-          if (suppresses_xywlr(qa, squad[i], thresh, nullptr)) t |= 1ULL << i;
-      } else {
-        for (int i = start; i < col_size; i++)
-          if (iou_axis_aligned(cur_box, sbox + i * 5) > thresh) t |= 1ULL << i;
       }
-      mask[(size_t)cur * col_blocks + col] = t;
+      const unsigned int word = __ballot_sync(0xffffffffu, bit);
+      if ((threadIdx.x & 31) == 0)
+        mask32[((size_t)cur * col_blocks + col) * 2 + ((threadIdx.x >> 5) & 1)] = word;
     }
   }
 }
@@ -446,14 +465,14 @@ static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* 
     return D3B_ERR_WORKSPACE;
   }
   unsigned long long* mask = (unsigned long long*)workspace;
-  const long long tri = (long long)col_blocks * (col_blocks + 1) / 2;
-  const int grid = (int)(tri < (long long)kNumSMs * 32 ? (tri > 0 ? tri : 1) : (long long)kNumSMs * 32);
+  const long long items = (long long)col_blocks * (col_blocks + 1) / 2 * kNmsSlices;
+  const int grid = (int)(items < (long long)kNumSMs * 16 ? (items > 0 ? items : 1) : (long long)kNumSMs * 16);
   if (fmt_kernel == 0)
-    nms_mask_kernel<0><<<grid, kNmsBlock, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<0><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   else if (fmt_kernel == 1)
-    nms_mask_kernel<1><<<grid, kNmsBlock, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<1><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   else
-    nms_mask_kernel<2><<<grid, kNmsBlock, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<2><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   D3B_LAUNCH_CHECK();
   const size_t smem = (size_t)col_blocks * 8;
   if (smem > 200 * 1024) {

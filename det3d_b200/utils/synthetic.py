@@ -84,3 +84,45 @@ def randomize_bn_(model, seed=0):
                 m.weight.data.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
                 m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
     return model
+
+
+def variance_preserving_init_(model, seed=0, sparse_fan_in_taps=6.0):
+    """He-style re-initialisation so that random-weight activations keep O(1) variance through the
+    sparse encoder and the RPN (the default inits shrink the signal to a spatially constant map, which
+    would leave NMS with ~70k tied scores -- a degenerate benchmark workload)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        w = getattr(m, "weight", None)
+        if w is None or w.dim() < 4:
+            continue
+        if w.dim() == 5:                      # sparse conv [kd,kh,kw,Cin,Cout]: only a few taps are occupied
+            k = w.shape[0] * w.shape[1] * w.shape[2]
+            fan_in = w.shape[3] * min(float(k), sparse_fan_in_taps)
+        else:                                 # Conv2d / ConvTranspose2d [Cout,Cin,kh,kw]
+            fan_in = w.shape[1] * w.shape[2] * w.shape[3]
+        with torch.no_grad():
+            w.copy_(torch.randn(w.shape, generator=g) * (2.0 / fan_in) ** 0.5)
+    return model
+
+
+def demo_weights_(model, seed=0, cls_scale=0.005, cls_bias=-1.05, box_scale=0.005):
+    """Random-init weights of the configured architecture that give a *non-degenerate* detection
+    workload (no checkpoints exist offline): variance-preserving conv init, random BN statistics, and
+    head scales calibrated (on 20k-point lidar-like clouds, CPU oracle) so that ~3 % of the anchors pass
+    the 0.3 score threshold with well-spread scores and finite decoded boxes."""
+    import torch
+
+    variance_preserving_init_(model, seed)
+    randomize_bn_(model, seed)
+    with torch.no_grad():
+        for m in model.modules():          # residual blocks: damp the branch so activations stay O(1..10)
+            if hasattr(m, "bn2") and hasattr(m, "conv2"):
+                m.bn2.weight.mul_(0.25)
+        for task in model.bbox_head.tasks:
+            task.conv_cls.weight.mul_(cls_scale)
+            task.conv_cls.bias.fill_(cls_bias)
+            task.conv_box.weight.mul_(box_scale)
+            task.conv_box.bias.zero_()
+    return model

