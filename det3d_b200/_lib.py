@@ -61,6 +61,22 @@ class ConvParams(C.Structure):
     ]
 
 
+class PredictParams(C.Structure):
+    _fields_ = [
+        ("cls", C.c_void_p), ("cls_row_stride", C.c_int32), ("cls_col0", C.c_int32),
+        ("box", C.c_void_p), ("box_row_stride", C.c_int32), ("box_col0", C.c_int32),
+        ("dir", C.c_void_p), ("dir_row_stride", C.c_int32), ("dir_col0", C.c_int32),
+        ("anchors", C.c_void_p),
+        ("batch", C.c_int32), ("hw", C.c_int32), ("na", C.c_int32), ("n_cls", C.c_int32), ("code", C.c_int32),
+        ("nd", C.c_int32),
+        ("vec_encode", C.c_int32), ("smooth_dim", C.c_int32), ("norm_velo", C.c_int32),
+        ("use_rotate_nms", C.c_int32), ("pre_max", C.c_int32), ("post_max", C.c_int32),
+        ("nms_iou_threshold", C.c_float), ("score_threshold", C.c_float), ("direction_offset", C.c_float),
+        ("post_center_range", C.c_float * 6), ("has_range", C.c_int32),
+        ("label_offset", C.c_int32),
+    ]
+
+
 _I3 = C.c_int32 * 3
 _vp, _i32, _i64, _sz, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
 
@@ -81,6 +97,8 @@ SIGNATURES = {
     "d3b_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_sparse_to_bev_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_rulebook_dense2d": (C.c_int, [_i32, _i32, _i32, C.c_int32 * 2, C.c_int32 * 2, _vp, _vp, _vp, _vp]),
+    "d3b_predict_workspace_bytes": (_sz, [C.POINTER(PredictParams)]),
+    "d3b_predict_task": (C.c_int, [C.POINTER(PredictParams), _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "d3b_boxes_iou_bev": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "d3b_nms_workspace_bytes": (_sz, [_i32]),
     "d3b_rotate_nms": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -95,6 +95,8 @@ class InferencePipeline:
     @staticmethod
     def pack(det):
         """-> one [B, D, nd+3] f32 tensor: box, score, label, valid (the D2H / all-gather payload)."""
+        if "packed" in det:
+            return det["packed"]
         return torch.cat([det["boxes"], det["scores"].unsqueeze(-1), det["labels"].float().unsqueeze(-1),
                           det["valid"].float().unsqueeze(-1)], dim=-1).contiguous()
 

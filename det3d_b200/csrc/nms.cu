@@ -403,24 +403,36 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
 }
 
 // Greedy sweep on the device (iou3d.cpp:103-116 semantics), one CTA.
-// remv lives in dynamic shared memory; stops as soon as max_keep boxes are kept.
+// `remv` lives in dynamic shared memory; stops as soon as max_keep boxes are kept.  When the upper
+// triangle of the mask fits in shared memory (N <= ~1400, i.e. always at the detector's operating
+// point of 1000 boxes) it is staged there with coalesced loads first, so the serial block-by-block
+// resolve never waits on global memory.
 __global__ void __launch_bounds__(1024)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const int* __restrict__ n_dev,
                  int col_blocks_alloc, int max_keep, long long* __restrict__ keep_idx,
-                 int* __restrict__ keep_count) {
+                 int* __restrict__ keep_count, int stage_mask) {
   extern __shared__ unsigned long long remv[];
   __shared__ unsigned long long diag[kNmsBlock];
   __shared__ unsigned long long kept_word;
   __shared__ int kept_total;
   const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int nb = (n + kNmsBlock - 1) / kNmsBlock;
+  unsigned long long* smask = remv + col_blocks_alloc;      // [n][nb] when stage_mask
   for (int j = threadIdx.x; j < nb; j += blockDim.x) remv[j] = 0ULL;
   if (threadIdx.x == 0) kept_total = 0;
+  if (stage_mask) {
+    for (int e = threadIdx.x; e < n * nb; e += blockDim.x) {
+      const int i = e / nb, j = e - i * nb;
+      smask[e] = j >= (i >> 6) ? mask[(size_t)i * col_blocks_alloc + j] : 0ULL;
+    }
+  }
   __syncthreads();
   for (int b = 0; b < nb; ++b) {
     const int in_block = min(n - b * kNmsBlock, kNmsBlock);
-    if ((int)threadIdx.x < in_block)
-      diag[threadIdx.x] = mask[(size_t)(b * kNmsBlock + threadIdx.x) * col_blocks_alloc + b];
+    if ((int)threadIdx.x < in_block) {
+      const int i = b * kNmsBlock + threadIdx.x;
+      diag[threadIdx.x] = stage_mask ? smask[(size_t)i * nb + b] : mask[(size_t)i * col_blocks_alloc + b];
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long cur = remv[b], kept = 0ULL;
@@ -445,7 +457,8 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
         while (bits) {
           const int i = __ffsll((long long)bits) - 1;
           bits &= bits - 1;
-          acc |= mask[(size_t)(b * kNmsBlock + i) * col_blocks_alloc + j];
+          const int row = b * kNmsBlock + i;
+          acc |= stage_mask ? smask[(size_t)row * nb + j] : mask[(size_t)row * col_blocks_alloc + j];
         }
         remv[j] = acc;
       }
@@ -474,14 +487,21 @@ static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* 
   else
     nms_mask_kernel<2><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   D3B_LAUNCH_CHECK();
-  const size_t smem = (size_t)col_blocks * 8;
+  size_t smem = (size_t)col_blocks * 8;
   if (smem > 200 * 1024) {
     set_error("nms: %d boxes exceed the single-CTA sweep capacity", n_cap);
     return D3B_ERR_UNSUPPORTED;
   }
-  if (smem > 48 * 1024)
-    D3B_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_sweep_kernel<<<1, 1024, smem, stream>>>(mask, n_cap, n_dev, col_blocks, max_keep, keep_idx, keep_count);
+  const size_t staged = smem + (size_t)n_cap * col_blocks * 8;
+  const int stage_mask = staged <= 200 * 1024 ? 1 : 0;
+  if (stage_mask) smem = staged;
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    D3B_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_attr = 200 * 1024;
+  }
+  nms_sweep_kernel<<<1, 1024, smem, stream>>>(mask, n_cap, n_dev, col_blocks, max_keep, keep_idx, keep_count,
+                                              stage_mask);
   D3B_LAUNCH_CHECK();
   return D3B_OK;
 }

@@ -1,0 +1,364 @@
+// Device-resident detection post-processing for one task head, whole batch, fixed shapes.
+//
+// Replaces the per-sample Python loop of MultiGroupHead.get_task_detections
+// (det3d/models/bbox_heads/mg_head.py:805-1085, use_multi_class_nms=False branch):
+//   sigmoid scores -> score filter -> top-`nms_pre_max_size` -> anchor decode
+//   (det3d/core/bbox/box_torch_ops.py:80-148) -> rotated NMS (-> csrc/nms.cu) ->
+//   direction fix -> post_center_limit_range mask,
+// as five launches over fixed-size buffers:
+//   P1 head_scores     best logit / label per anchor straight from the (possibly strided) head rows
+//   P2 topk_select     one CTA per sample: 4-pass radix select of the k-th largest logit, ordered
+//                      gather of the winners, bitonic sort (value desc, index asc)
+//   P3 decode_selected decode ONLY the k selected anchors (the reference decodes all 70,400),
+//                      sigmoid, direction label, count of scores >= threshold (a prefix, scores are sorted)
+//   -- d3b_rotate_nms / d3b_normal_nms on the k candidates (n_valid read on the device) --
+//   P4 finalize        gather the kept boxes, direction flip, range mask -> packed [B, post, nd+3] rows
+// Selection is identical to the reference's "filter, then top-k": sigmoid is monotonic, so the
+// passing set is a prefix of the top-k by logit.
+#include "common.cuh"
+
+namespace d3b {
+
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMax = 2048;
+
+__device__ __forceinline__ unsigned int float_to_ordered(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending order as unsigned
+}
+
+// ---- P1 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_scores_kernel(const float* __restrict__ cls, int row_stride, int col0, int batch, int hw, int na,
+                   int n_cls, float* __restrict__ best_logit, unsigned char* __restrict__ best_label) {
+  const int A = hw * na;
+  const long long total = (long long)batch * A;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / A), i = (int)(e - (long long)b * A);
+    const int cell = i / na, a = i - cell * na;
+    const float* p = cls + ((size_t)b * hw + cell) * row_stride + col0 + a * n_cls;
+    float best = p[0];
+    int lab = 0;
+    for (int c = 1; c < n_cls; ++c) {
+      const float v = p[c];
+      if (v > best) { best = v; lab = c; }    // first maximum wins, like torch.max
+    }
+    best_logit[e] = best;
+    best_label[e] = (unsigned char)lab;
+  }
+}
+
+// ---- P2 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTopkThreads)
+topk_select_kernel(const float* __restrict__ values, int A, int k, float* __restrict__ out_val,
+                   int* __restrict__ out_idx) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_remaining;
+  __shared__ unsigned int sel_key[kTopkMax];
+  __shared__ int sel_idx[kTopkMax];
+  __shared__ int s_count, s_ties_taken;
+  __shared__ int warp_tot[32];
+  const float* v = values + (size_t)blockIdx.x * A;
+  float* ov = out_val + (size_t)blockIdx.x * k;
+  int* oi = out_idx + (size_t)blockIdx.x * k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // radix select: find the key of the k-th largest element
+  if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned int)k; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int j = tid; j < 256; j += kTopkThreads) hist[j] = 0u;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const unsigned int pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < A; i += kTopkThreads) {
+      const unsigned int key = float_to_ordered(v[i]);
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int rem = s_remaining, d = 255;
+      for (;; --d) {                       // walk digits from the top
+        const unsigned int c = hist[d];
+        if (c >= rem || d == 0) break;
+        rem -= c;
+      }
+      s_prefix = prefix | (d << shift);
+      s_remaining = rem;                   // how many elements equal to the pivot digit-prefix are still needed
+    }
+    __syncthreads();
+  }
+  const unsigned int pivot = s_prefix;     // key of the k-th largest
+  const int ties_needed = (int)s_remaining;
+  if (tid == 0) { s_count = 0; s_ties_taken = 0; }
+  __syncthreads();
+  // winners strictly above the pivot: order is fixed by the sort below
+  for (int i = tid; i < A; i += kTopkThreads) {
+    const unsigned int key = float_to_ordered(v[i]);
+    if (key > pivot) {
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < kTopkMax) { sel_key[pos] = key; sel_idx[pos] = i; }
+    }
+  }
+  __syncthreads();
+  const int n_gt = s_count;
+  // ties: the lowest indices win (deterministic): ordered pass in chunks of kTopkThreads
+  for (int base = 0; base < A && s_ties_taken < ties_needed; base += kTopkThreads) {
+    const int i = base + tid;
+    const bool tie = i < A && float_to_ordered(v[i]) == pivot;
+    const unsigned int bal = __ballot_sync(0xffffffffu, tie);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_ties_taken;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    const int rank = before + __popc(bal & ((1u << lane) - 1u));
+    if (tie && rank < ties_needed) { sel_key[n_gt + rank] = pivot; sel_idx[n_gt + rank] = i; }
+    __syncthreads();
+    if (tid == 0) {
+      int t = s_ties_taken;
+      for (int w = 0; w < kTopkThreads / 32; ++w) t += warp_tot[w];
+      s_ties_taken = t;
+    }
+    __syncthreads();
+  }
+  // pad to a power of two and bitonic-sort descending by (key, -index)
+  int n2 = 1;
+  while (n2 < k) n2 <<= 1;
+  for (int j = k + tid; j < n2; j += kTopkThreads) { sel_key[j] = 0u; sel_idx[j] = 0x7fffffff; }
+  __syncthreads();
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < n2 / 2; t += kTopkThreads) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned int ka = sel_key[lo], kb = sel_key[hi];
+        const int ia = sel_idx[lo], ib = sel_idx[hi];
+        const bool a_first = ka > kb || (ka == kb && ia < ib);   // a should precede b in descending order
+        if (a_first != desc) { sel_key[lo] = kb; sel_key[hi] = ka; sel_idx[lo] = ib; sel_idx[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += kTopkThreads) {
+    const unsigned int key = sel_key[j];
+    const unsigned int u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    ov[j] = __uint_as_float(u);
+    oi[j] = sel_idx[j];
+  }
+}
+
+// ---- P3 -------------------------------------------------------------------------------------
+struct PredictDev {
+  const float* box; int box_stride, box_col0;
+  const float* dir; int dir_stride, dir_col0;
+  const float* anchors;
+  const unsigned char* best_label;
+  int batch, hw, na, code, nd, k, post;
+  int vec_encode, smooth_dim, norm_velo, use_rotate;
+  float score_thr, direction_offset;
+  float range[6];
+  int has_range, label_offset;
+};
+
+__global__ void __launch_bounds__(256)
+decode_selected_kernel(PredictDev p, const float* __restrict__ sel_logit, const int* __restrict__ sel_idx,
+                       float* __restrict__ cand, float* __restrict__ nms_boxes, float* __restrict__ scores,
+                       int* __restrict__ labels, int* __restrict__ dir_labels, int* __restrict__ n_valid) {
+  const int A = p.hw * p.na;
+  const int total = p.batch * p.k;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int b = e / p.k;
+    const int i = sel_idx[e];
+    const int cell = i / p.na, a = i - cell * p.na;
+    const float* t = p.box + ((size_t)b * p.hw + cell) * p.box_stride + p.box_col0 + a * p.code;
+    const float* an = p.anchors + (size_t)i * p.nd;
+    // box_torch_ops.py:80-148
+    const float xa = an[0], ya = an[1], za = an[2], wa = an[3], la = an[4], ha = an[5], ra = an[p.nd - 1];
+    // same fp32 op sequence as the torch expression tree (separate mul / add kernels: no FMA contraction)
+    const float diagonal = sqrtf(__fadd_rn(__fmul_rn(la, la), __fmul_rn(wa, wa)));
+    float* o = cand + (size_t)e * p.nd;
+    const float xg = __fadd_rn(__fmul_rn(t[0], diagonal), xa);
+    const float yg = __fadd_rn(__fmul_rn(t[1], diagonal), ya);
+    const float zg = __fadd_rn(__fmul_rn(t[2], ha), za);
+    float wg, lg, hg;
+    if (p.smooth_dim) {
+      lg = __fmul_rn(__fadd_rn(t[4], 1.0f), la); wg = __fmul_rn(__fadd_rn(t[3], 1.0f), wa); hg = __fmul_rn(__fadd_rn(t[5], 1.0f), ha);
+    } else {
+      lg = __fmul_rn(expf(t[4]), la); wg = __fmul_rn(expf(t[3]), wa); hg = __fmul_rn(expf(t[5]), ha);
+    }
+    o[0] = xg; o[1] = yg; o[2] = zg; o[3] = wg; o[4] = lg; o[5] = hg;
+    int q = 6;
+    if (p.nd == 9) {
+      const float vxa = an[6], vya = an[7];
+      if (p.norm_velo) { o[6] = __fadd_rn(__fmul_rn(t[6], diagonal), vxa); o[7] = __fadd_rn(__fmul_rn(t[7], diagonal), vya); }
+      else { o[6] = __fadd_rn(t[6], vxa); o[7] = __fadd_rn(t[7], vya); }
+      q = 8;
+    }
+    float rg;
+    if (p.vec_encode) rg = atan2f(__fadd_rn(t[q + 1], sinf(ra)), __fadd_rn(t[q], cosf(ra)));
+    else rg = __fadd_rn(t[q], ra);
+    o[p.nd - 1] = rg;
+    float* nb = nms_boxes + (size_t)e * 5;
+    if (p.use_rotate) {
+      nb[0] = xg; nb[1] = yg; nb[2] = wg; nb[3] = lg; nb[4] = rg;      // mg_head.py:1008
+    } else {
+      // center_to_corner_box2d + corner_to_standup_nd (box_torch_ops / box_np_ops.py:267-340,419-497)
+      const float s = sinf(rg), c = cosf(rg);
+      const float ox[4] = {-0.5f, -0.5f, 0.5f, 0.5f}, oy[4] = {-0.5f, 0.5f, 0.5f, -0.5f};
+      float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float px = wg * ox[c4], py = lg * oy[c4];
+        const float cx = px * c + py * s + xg, cy = -px * s + py * c + yg;
+        mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx); mny = fminf(mny, cy); mxy = fmaxf(mxy, cy);
+      }
+      nb[0] = mnx; nb[1] = mny; nb[2] = mxx; nb[3] = mxy; nb[4] = 0.0f;
+    }
+    const float sc = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sel_logit[e])));   // torch.sigmoid in fp32
+    scores[e] = sc;
+    labels[e] = (int)p.best_label[(size_t)b * A + i] + p.label_offset;
+    if (p.dir != nullptr) {
+      const float* d = p.dir + ((size_t)b * p.hw + cell) * p.dir_stride + p.dir_col0 + a * 2;
+      dir_labels[e] = d[1] > d[0] ? 1 : 0;                            // torch.max: first maximum wins
+    }
+    if (!(p.score_thr > 0.0f) || sc >= p.score_thr) atomicAdd(&n_valid[b], 1);
+  }
+}
+
+// ---- P4 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+finalize_kernel(PredictDev p, const float* __restrict__ cand, const float* __restrict__ scores,
+                const int* __restrict__ labels, const int* __restrict__ dir_labels,
+                const long long* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                float* __restrict__ packed, int packed_stride /* rows per sample in `packed` */, int row_offset) {
+  const int total = p.batch * p.post;
+  const int width = p.nd + 3;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int b = e / p.post, j = e - b * p.post;
+    float* o = packed + ((size_t)b * packed_stride + row_offset + j) * width;
+    const bool have = j < keep_count[b];
+    if (!have) {
+      for (int c = 0; c < width; ++c) o[c] = 0.0f;
+      continue;
+    }
+    const int src = b * p.k + (int)keep_idx[(size_t)b * p.post + j];
+    const float* bx = cand + (size_t)src * p.nd;
+    for (int c = 0; c < p.nd; ++c) o[c] = bx[c];
+    if (p.dir != nullptr) {
+      const bool opp = ((bx[p.nd - 1] - p.direction_offset) > 0.0f) != (dir_labels[src] != 0);   // mg_head.py:1044-1051
+      if (opp) o[p.nd - 1] = __fadd_rn(bx[p.nd - 1], 3.14159265358979323846f);
+    }
+    bool ok = true;
+    if (p.has_range) {
+      for (int c = 0; c < 3; ++c) ok = ok && (o[c] >= p.range[c]) && (o[c] <= p.range[3 + c]);     // :1055-1063
+    }
+    o[p.nd] = scores[src];
+    o[p.nd + 1] = (float)labels[src];
+    o[p.nd + 2] = ok ? 1.0f : 0.0f;
+  }
+}
+
+struct PredictWs {
+  float* best_logit; unsigned char* best_label; float* sel_logit; int* sel_idx; float* cand; float* nms_boxes;
+  float* scores; int* labels; int* dir_labels; int* n_valid; long long* keep_idx; int* keep_count; char* nms_ws;
+  size_t nms_ws_bytes, bytes;
+};
+
+static PredictWs carve_predict(const d3b_predict_params* q, char* base) {
+  PredictWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base ? base + o : (char*)nullptr; };
+  const size_t A = (size_t)q->hw * q->na, B = q->batch, k = q->pre_max, post = q->post_max;
+  w.best_logit = (float*)take(B * A * 4);
+  w.best_label = (unsigned char*)take(B * A);
+  w.sel_logit = (float*)take(B * k * 4);
+  w.sel_idx = (int*)take(B * k * 4);
+  w.cand = (float*)take(B * k * q->nd * 4);
+  w.nms_boxes = (float*)take(B * k * 5 * 4);
+  w.scores = (float*)take(B * k * 4);
+  w.labels = (int*)take(B * k * 4);
+  w.dir_labels = (int*)take(B * k * 4);
+  w.n_valid = (int*)take(B * 4);
+  w.keep_idx = (long long*)take(B * post * 8);
+  w.keep_count = (int*)take(B * 4);
+  w.nms_ws_bytes = d3b_nms_workspace_bytes((int32_t)k);
+  w.nms_ws = take(w.nms_ws_bytes);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+
+static int check_predict(const d3b_predict_params* q) {
+  D3B_REQUIRE(q && q->cls && q->box && q->anchors, "d3b_predict_task: null argument");
+  D3B_REQUIRE(q->batch >= 1 && q->hw >= 1 && q->na >= 1 && q->n_cls >= 1 && q->n_cls <= 255,
+              "d3b_predict_task: bad head shape");
+  D3B_REQUIRE(q->nd == 7 || q->nd == 9, "d3b_predict_task: boxes must have 7 or 9 values, got %d", q->nd);
+  D3B_REQUIRE(q->code == q->nd + (q->vec_encode ? 1 : 0), "d3b_predict_task: code size %d does not match nd %d", q->code, q->nd);
+  D3B_REQUIRE(q->pre_max >= 1 && q->pre_max <= kTopkMax && q->pre_max <= q->hw * q->na,
+              "d3b_predict_task: nms_pre_max_size %d outside [1, min(%d, anchors)]", q->pre_max, kTopkMax);
+  D3B_REQUIRE(q->post_max >= 1 && q->post_max <= q->pre_max, "d3b_predict_task: bad nms_post_max_size");
+  return D3B_OK;
+}
+
+extern "C" size_t d3b_predict_workspace_bytes(const d3b_predict_params* q) {
+  if (!q || q->batch < 1 || q->hw < 1 || q->na < 1 || q->pre_max < 1 || q->post_max < 1) return 0;
+  return carve_predict(q, nullptr).bytes;
+}
+
+extern "C" int d3b_predict_task(const d3b_predict_params* q, float* packed, int32_t packed_rows_per_sample,
+                                int32_t row_offset, int32_t* keep_counts, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int st = check_predict(q);
+  if (st != D3B_OK) return st;
+  D3B_REQUIRE(packed && workspace, "d3b_predict_task: null output/workspace");
+  D3B_REQUIRE(row_offset >= 0 && row_offset + q->post_max <= packed_rows_per_sample, "d3b_predict_task: packed rows overflow");
+  PredictWs w = carve_predict(q, (char*)workspace);
+  if (w.bytes > workspace_bytes) {
+    set_error("d3b_predict_task: workspace %zu < %zu", workspace_bytes, w.bytes);
+    return D3B_ERR_WORKSPACE;
+  }
+  const int A = q->hw * q->na;
+  PredictDev p;
+  p.box = q->box; p.box_stride = q->box_row_stride; p.box_col0 = q->box_col0;
+  p.dir = q->dir; p.dir_stride = q->dir_row_stride; p.dir_col0 = q->dir_col0;
+  p.anchors = q->anchors; p.best_label = w.best_label;
+  p.batch = q->batch; p.hw = q->hw; p.na = q->na; p.code = q->code; p.nd = q->nd; p.k = q->pre_max; p.post = q->post_max;
+  p.vec_encode = q->vec_encode; p.smooth_dim = q->smooth_dim; p.norm_velo = q->norm_velo; p.use_rotate = q->use_rotate_nms;
+  p.score_thr = q->score_threshold; p.direction_offset = q->direction_offset;
+  for (int c = 0; c < 6; ++c) p.range[c] = q->post_center_range[c];
+  p.has_range = q->has_range; p.label_offset = q->label_offset;
+
+  head_scores_kernel<<<grid_for((long long)q->batch * A, 256), 256, 0, stream>>>(
+      q->cls, q->cls_row_stride, q->cls_col0, q->batch, q->hw, q->na, q->n_cls, w.best_logit, w.best_label);
+  D3B_LAUNCH_CHECK();
+  topk_select_kernel<<<q->batch, kTopkThreads, 0, stream>>>(w.best_logit, A, q->pre_max, w.sel_logit, w.sel_idx);
+  D3B_LAUNCH_CHECK();
+  D3B_CUDA(cudaMemsetAsync(w.n_valid, 0, (size_t)q->batch * 4, stream));
+  decode_selected_kernel<<<grid_for((long long)q->batch * q->pre_max, 256), 256, 0, stream>>>(
+      p, w.sel_logit, w.sel_idx, w.cand, w.nms_boxes, w.scores, w.labels, w.dir_labels, w.n_valid);
+  D3B_LAUNCH_CHECK();
+  for (int b = 0; b < q->batch; ++b) {
+    const float* boxes = w.nms_boxes + (size_t)b * q->pre_max * 5;
+    if (q->use_rotate_nms)
+      st = d3b_rotate_nms(boxes, q->pre_max, w.n_valid + b, D3B_BOX_XYWLR, q->nms_iou_threshold, q->post_max,
+                          (int64_t*)(w.keep_idx + (size_t)b * q->post_max), w.keep_count + b, w.nms_ws,
+                          w.nms_ws_bytes, stream);
+    else
+      st = d3b_normal_nms(boxes, q->pre_max, w.n_valid + b, q->nms_iou_threshold, q->post_max,
+                          (int64_t*)(w.keep_idx + (size_t)b * q->post_max), w.keep_count + b, w.nms_ws,
+                          w.nms_ws_bytes, stream);
+    if (st != D3B_OK) return st;
+  }
+  finalize_kernel<<<grid_for((long long)q->batch * q->post_max, 128), 128, 0, stream>>>(
+      p, w.cand, w.scores, w.labels, w.dir_labels, w.keep_idx, w.keep_count, packed, packed_rows_per_sample,
+      row_offset);
+  D3B_LAUNCH_CHECK();
+  if (keep_counts) D3B_CUDA(cudaMemcpyAsync(keep_counts, w.keep_count, (size_t)q->batch * 4, cudaMemcpyDeviceToDevice, stream));
+  return D3B_OK;
+}

@@ -249,32 +249,44 @@ rb_scan_prefix(const unsigned int* __restrict__ bitmap, long long n_words,
   }
 }
 
-// emit pass: one warp per bitmap word, lane = bit -> coordinates of every set bit at its rank.
-// (A thread-per-word loop serialises up to 128 stores in dense regions; this does not.)
+// emit pass: a warp takes 32 bitmap words at a time; each lane decomposes ITS word's first cell once
+// (the only 64-bit divisions), then the warp expands the non-zero words one by one, lane = bit, with
+// carry arithmetic instead of divisions.
 __global__ void __launch_bounds__(256)
 rb_emit_coors(const unsigned int* __restrict__ bitmap, const int* __restrict__ word_prefix, long long n_words,
               SiteIndexDev out, int out_cap, int* __restrict__ out_coors) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  // each warp scans 32 words at a time: lane l tests word (chunk*32 + l), then the warp expands the non-zero ones
   for (long long chunk = warp0; chunk * 32 < n_words; chunk += n_warps) {
     const long long wi = chunk * 32 + lane;
     const unsigned int mine = wi < n_words ? bitmap[wi] : 0u;
+    int x0 = 0, y0 = 0, z0 = 0, b0 = 0, pref = 0;
+    if (mine != 0u) {
+      unsigned long long lin = (unsigned long long)wi << 5;
+      x0 = (int)(lin % out.W); lin /= out.W;
+      y0 = (int)(lin % out.H); lin /= out.H;
+      z0 = (int)(lin % out.D);
+      b0 = (int)(lin / out.D);
+      pref = word_prefix[wi];
+    }
     unsigned int nz = __ballot_sync(0xffffffffu, mine != 0u);
     while (nz) {
       const int src = __ffs(nz) - 1;
       nz &= nz - 1;
       const unsigned int bits = __shfl_sync(0xffffffffu, mine, src);
-      const long long w = chunk * 32 + src;
+      int x = __shfl_sync(0xffffffffu, x0, src) + lane;
+      int y = __shfl_sync(0xffffffffu, y0, src);
+      int z = __shfl_sync(0xffffffffu, z0, src);
+      int bb = __shfl_sync(0xffffffffu, b0, src);
+      const int base_rank = __shfl_sync(0xffffffffu, pref, src);
       if ((bits >> lane) & 1u) {
-        const int rank = word_prefix[w] + __popc(bits & ((1u << lane) - 1u));
+        const int rank = base_rank + __popc(bits & ((1u << lane) - 1u));
         if (rank < out_cap) {
-          unsigned long long lin = ((unsigned long long)w << 5) + lane;
-          const int x = (int)(lin % out.W); lin /= out.W;
-          const int y = (int)(lin % out.H); lin /= out.H;
-          const int z = (int)(lin % out.D);
-          const int bb = (int)(lin / out.D);
+          while (x >= out.W) {
+            x -= out.W;
+            if (++y >= out.H) { y = 0; if (++z >= out.D) { z = 0; ++bb; } }
+          }
           *reinterpret_cast<int4*>(out_coors + (size_t)rank * 4) = make_int4(bb, z, y, x);
         }
       }

@@ -200,6 +200,36 @@ int d3b_normal_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev
                    int32_t max_keep, int64_t* keep_idx, int32_t* keep_count, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ========================================================================= *
+ * 5. Detection post-processing of one task head (whole batch, fixed shapes)
+ *    replaces MultiGroupHead.get_task_detections, det3d/models/bbox_heads/mg_head.py:805-1085
+ *    (use_multi_class_nms = False), incl. second_box_decode (core/bbox/box_torch_ops.py:80-148)
+ *    and rotate_nms (:528-549).  Head tensors are addressed as rows: element (b, cell, j) lives
+ *    at ptr[(b*hw + cell) * row_stride + col0 + j], so both NHWC-permuted tensors and column
+ *    slices of a fused [B*H*W, 32] row buffer work without a copy.
+ * ========================================================================= */
+typedef struct {
+  const float* cls;  int32_t cls_row_stride, cls_col0;   /* logits, na*n_cls per cell          */
+  const float* box;  int32_t box_row_stride, box_col0;   /* encodings, na*code per cell        */
+  const float* dir;  int32_t dir_row_stride, dir_col0;   /* direction logits, na*2, or NULL     */
+  const float* anchors;                                   /* [hw*na, nd], shared by the batch    */
+  int32_t batch, hw, na, n_cls, code, nd;
+  int32_t vec_encode, smooth_dim, norm_velo;              /* box coder flags                     */
+  int32_t use_rotate_nms, pre_max, post_max;              /* test_cfg.nms                        */
+  float nms_iou_threshold, score_threshold, direction_offset;
+  float post_center_range[6]; int32_t has_range;
+  int32_t label_offset;                                   /* added to the class index            */
+} d3b_predict_params;
+
+size_t d3b_predict_workspace_bytes(const d3b_predict_params* p);
+
+/* packed [batch, packed_rows_per_sample, nd+3] f32: rows [row_offset, row_offset+post_max) of every
+ * sample receive box[nd], score, label, valid(0/1); rows beyond the kept count are zero.
+ * keep_counts [batch] i32 (optional) = boxes surviving NMS (before the range mask). */
+int d3b_predict_task(const d3b_predict_params* p, float* packed, int32_t packed_rows_per_sample,
+                     int32_t row_offset, int32_t* keep_counts, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

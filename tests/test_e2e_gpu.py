@@ -180,3 +180,58 @@ def test_cbgs_nuscenes_config_batch2():
         j = d.argmin(1)
         ok = (d.min(1)[0] <= 2e-3) & (gl[j] == wl)
         assert int(ok.sum()) >= 0.9 * wb.shape[0]
+
+
+def test_fused_predict_kernels_match_torch_ops(setup):
+    """d3b_predict_task (radix-select top-k, decode of the selected anchors, NMS, finalize) vs the same
+    algorithm written with torch ops: identical boxes / scores / labels / validity."""
+    from det3d_b200.utils.synthetic import lidar_like_cloud
+    cfg, pipe, cpu = setup
+    model = pipe.model
+    for seed in (3, 4):
+        pts = torch.from_numpy(lidar_like_cloud(20000, cfg.voxel_generator.range, 4, seed)).cuda()
+        vox = pipe.voxelizer(pts, [0, 20000])
+        with torch.no_grad():
+            rows, (b, h, w) = model.backbone.forward_rows(vox["mean"], vox["coors"], 1, [int(g) for g in pipe.grid_size],
+                                                          n_dev=vox["counts"][1:2])
+            preds = model.fused_bev().run(rows, b, h, w)
+            example = dict(anchors=pipe.anchors(1))
+            a = model.bbox_head.predict_device(example, preds, cfg.test_cfg)
+            t = model.bbox_head.predict_device(example, preds, cfg.test_cfg, use_torch_ops=True)
+        va, vt = a["valid"][0], t["valid"][0]
+        assert int(vt.sum()) >= 10
+        assert torch.equal(va, vt)
+        assert torch.equal(a["boxes"][0][va], t["boxes"][0][vt])          # same fp32 op sequence -> bit-identical
+        assert torch.equal(a["scores"][0][va], t["scores"][0][vt])
+        assert torch.equal(a["labels"][0][va], t["labels"][0][vt])
+
+
+def test_topk_handles_ties_and_constants():
+    """All-equal scores (the degenerate case): lowest anchor indices win, deterministically."""
+    import ctypes as C
+    from det3d_b200 import _lib
+    B, hw, na = 2, 3000, 2
+    cls = torch.zeros((B, 1, hw, na), device="cuda")
+    cls[1] = -5.0
+    cls[1, 0, 100:110, :] = 5.0
+    box = torch.zeros((B, 1, hw, na * 7), device="cuda")
+    anchors = torch.rand((hw * na, 7), device="cuda") * 10 + 1
+    q = _lib.PredictParams()
+    q.cls, q.cls_row_stride, q.cls_col0 = cls.data_ptr(), na, 0
+    q.box, q.box_row_stride, q.box_col0 = box.data_ptr(), na * 7, 0
+    q.dir = None
+    q.anchors = anchors.data_ptr()
+    q.batch, q.hw, q.na, q.n_cls, q.code, q.nd = B, hw, na, 1, 7, 7
+    q.use_rotate_nms, q.pre_max, q.post_max = 1, 1000, 1000
+    q.nms_iou_threshold, q.score_threshold = 2.0, 0.3       # IoU never reaches 2 -> NMS keeps every candidate
+    q.has_range = 0
+    ws = torch.empty(_lib.lib().d3b_predict_workspace_bytes(C.byref(q)), dtype=torch.uint8, device="cuda")
+    packed = torch.zeros((B, 1000, 10), device="cuda")
+    counts = torch.zeros(B, dtype=torch.int32, device="cuda")
+    st = _lib.lib().d3b_predict_task(C.byref(q), packed.data_ptr(), 1000, 0, counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    torch.cuda.current_stream().cuda_stream)
+    _lib.check(st)
+    assert counts.tolist() == [1000, 20]                    # sample 0: 0.5 >= 0.3 for all; sample 1: only the 20 raised logits
+    got0 = packed[0, :, :3]
+    assert torch.equal(got0, anchors[:1000, :3])            # ties -> first 1000 anchors, in index order
+    assert torch.equal(packed[1, :20, :3], anchors[200:220, :3])
