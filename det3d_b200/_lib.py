@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdet3d_b200.so")
 D3B_OK = 0
 ALGO_SIMT = 0
 ALGO_TC = 1
+ALGO_TC_PAIRS = 2
 BOX_XYXYR = 0
 BOX_XYWLR = 1
 
@@ -58,6 +59,13 @@ class ConvParams(C.Structure):
         ("residual", C.c_void_p),
         ("relu", C.c_int32),
         ("algo", C.c_int32),
+        ("pair_in", C.c_void_p),
+        ("pair_out", C.c_void_p),
+        ("pair_count", C.c_void_p),
+        ("in_bias", C.c_void_p),
+        ("in_scale", C.c_void_p),
+        ("in_shift", C.c_void_p),
+        ("in_relu", C.c_int32),
     ]
 
 
@@ -94,6 +102,8 @@ SIGNATURES = {
     "d3b_conv_packed_weight_floats": (_sz, [_i32, _i32, _i32]),
     "d3b_conv_pack_weight": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "d3b_sparse_conv": (C.c_int, [_vp, _vp, _vp, _vp, _i32, C.POINTER(ConvParams), _vp, _vp]),
+    "d3b_rulebook_pairs": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "d3b_feature_epilogue": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "d3b_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_sparse_to_bev_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_rulebook_dense2d": (C.c_int, [_i32, _i32, _i32, C.c_int32 * 2, C.c_int32 * 2, _vp, _vp, _vp, _vp]),

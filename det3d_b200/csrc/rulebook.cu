@@ -294,6 +294,37 @@ rb_emit_coors(const unsigned int* __restrict__ bitmap, const int* __restrict__ w
   }
 }
 
+// ---- pair lists (classic rulebook form) ---------------------------------------------------
+// One thread per (k, o); a warp's valid entries of the same k take consecutive slots through one
+// warp-aggregated atomicAdd.  Pair order inside an offset is therefore arbitrary (as in spconv's GPU
+// rulebook); only the fp32 summation order of the atomics-based kernel depends on it.
+__global__ void __launch_bounds__(256)
+rb_compact_pairs(const int* __restrict__ nbr, const int* __restrict__ n_out, int out_cap, int k_vol,
+                 int* __restrict__ pair_in, int* __restrict__ pair_out, int* __restrict__ pair_count) {
+  const int n = min(*n_out, out_cap);
+  const long long total = (long long)n * k_vol;
+  for (long long e0 = (long long)blockIdx.x * blockDim.x; e0 < total; e0 += (long long)gridDim.x * blockDim.x) {
+    const long long e = e0 + threadIdx.x;
+    int k = -1, o = 0, src = -1;
+    if (e < total) {
+      k = (int)(e / n);
+      o = (int)(e - (long long)k * n);
+      src = nbr[(size_t)k * out_cap + o];
+    }
+    const bool valid = src >= 0;
+    const unsigned int peers = __match_any_sync(0xffffffffu, valid ? k : -1 - (int)(threadIdx.x & 31));
+    if (valid) {
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&pair_count[k], __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const int pos = base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+      pair_in[(size_t)k * out_cap + pos] = src;
+      pair_out[(size_t)k * out_cap + pos] = o;
+    }
+  }
+}
+
 static int check_geom(const int32_t ksize[3], KernelGeom* g) {
   g->kvol = ksize[0] * ksize[1] * ksize[2];
   for (int j = 0; j < 3; ++j) g->k[j] = ksize[j];
@@ -342,6 +373,19 @@ extern "C" int d3b_rulebook_subm(const int32_t* coors, const int32_t* n_rows, in
   D3B_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)div_up(row_cap, 128) * 4, stream));
   rb_neighbours<<<grid_for((long long)row_cap * g.kvol, 256), 256, 0, stream>>>(
       coors, n_rows, row_cap, to_dev(index, row_cap), g, nbr, tile_mask);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+extern "C" int d3b_rulebook_pairs(const int32_t* nbr, const int32_t* n_out, int32_t out_cap, int32_t k_vol,
+                                  int32_t* pair_in, int32_t* pair_out, int32_t* pair_count, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(nbr && n_out && pair_in && pair_out && pair_count, "d3b_rulebook_pairs: null argument");
+  D3B_REQUIRE(k_vol >= 1 && k_vol <= 32 && out_cap >= 0, "d3b_rulebook_pairs: bad shape");
+  D3B_CUDA(cudaMemsetAsync(pair_count, 0, (size_t)k_vol * 4, stream));
+  if (out_cap == 0) return D3B_OK;
+  rb_compact_pairs<<<grid_for((long long)out_cap * k_vol, 256), 256, 0, stream>>>(nbr, n_out, out_cap, k_vol, pair_in,
+                                                                              pair_out, pair_count);
   D3B_LAUNCH_CHECK();
   return D3B_OK;
 }

@@ -347,6 +347,275 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
   }
 }
 
+// =============================================================================================
+// Pair-based variant (D3B_ALGO_TC_PAIRS): spconv's classic "gather -> GEMM -> scatter-add" on the
+// tensor cores.  The output-stationary kernel above pads every (tile, offset) slot to 128 rows; at
+// lidar densities only ~1/3 of those rows have a neighbour, so 2/3 of the gather, shared-memory and
+// MMA work is padding.  Here the rulebook is first compacted per offset (d3b_rulebook_pairs) and a
+// work item is 128 VALID pairs of one offset: every A row is live.  The price: partial sums go to
+// the output rows with fp32 atomics (red.global.add.v4.f32), so the summation order -- not the
+// value within fp32 rounding -- varies run to run, and the layer's own bias/BN/ReLU cannot be fused
+// here; it is applied by the consumer while it gathers (in_bias/in_scale/in_shift/in_relu) or by
+// d3b_feature_epilogue.
+//
+// Roles: 2 gather groups x 4 warps (slots alternate), 1 MMA warp, 4 epilogue warps (TMEM -> red).
+// Two TMEM accumulators so the epilogue of item i overlaps the MMAs of item i+1.
+// =============================================================================================
+constexpr int kPairGroups = 2;
+constexpr int kPairMmaWarp = 4 * kPairGroups;           // warp 8
+constexpr int kPairEpiWarp0 = kPairMmaWarp + 1;         // warps 9..12 (warp % 4 = 1,2,3,0: one per TMEM quadrant)
+constexpr int kPairThreads = 32 * (kPairEpiWarp0 + 4);  // 416
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kPairThreads, 1)
+spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ pair_in,
+                    const int* __restrict__ pair_out, const int* __restrict__ pair_count, int out_cap, int k_vol,
+                    int c_in, int n_kb, const float* __restrict__ packed, const float* __restrict__ in_bias,
+                    const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu,
+                    float* __restrict__ feat_out) {
+  using Cfg = TcCfg<COUT>;
+  constexpr int kAccCols = COUT < 32 ? 32 : COUT;          // columns per accumulator
+  constexpr int kTmemCols = 2 * kAccCols;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+  int* chunk_prefix = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);   // [k_vol + 1]
+  int* count_s = chunk_prefix + 40;                                                                // [k_vol]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int run = 0;
+    for (int k = 0; k < k_vol; ++k) {
+      const int cnt = min(pair_count[k], out_cap);
+      count_s[k] = cnt;
+      chunk_prefix[k] = run;
+      run += (cnt + kTcTileM - 1) / kTcTileM;
+    }
+    chunk_prefix[k_vol] = run;
+  }
+  if (warp == kPairMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int n_items = chunk_prefix[k_vol];
+
+  auto item_k = [&](int item) {          // offset of a work item (k_vol <= 32 entries: linear walk)
+    int k = 0;
+    while (k + 1 < k_vol && chunk_prefix[k + 1] <= item) ++k;
+    return k;
+  };
+
+  if (warp < kPairMmaWarp) {
+    // ===================== gather producers =====================
+    // A group owns whole work items (alternating with the other group): one round trip for the
+    // 128 input-row indices, then the feature rows of TWO 32-channel slices are fetched together,
+    // so an item of a 64-channel layer costs two global round trips, not four.
+    const int group = warp >> 2, wq = warp & 3;
+    const int g = lane >> 3, c = lane & 7;
+    const bool issues_tma = (wq == 0 && lane == 0);
+    const bool has_act = in_scale != nullptr || in_bias != nullptr || in_relu;
+    uint32_t seq = 0;                     // CTA-local item ordinal
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++seq) {
+      if ((int)(seq % kPairGroups) != group) continue;
+      const int k = item_k(item);
+      const int first = (item - chunk_prefix[k]) * kTcTileM;
+      const int cnt = count_s[k];
+      const int* pin = pair_in + (size_t)k * out_cap + first;
+      int src[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int row = wq * 32 + 4 * q + g;
+        src[q] = first + row < cnt ? __ldg(pin + row) : -1;
+      }
+      for (int kb0 = 0; kb0 < n_kb; kb0 += 2) {
+        float4 v[2][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = (kb0 + h) * kTcKc + c * 4;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[h][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src[q] >= 0 && ch < c_in) v[h][q] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src[q] * c_in + ch));
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int kb = kb0 + h;
+          if (kb >= n_kb) break;
+          const int ch = kb * kTcKc + c * 4;
+          if (has_act && ch < c_in) {
+            // deferred epilogue of the producing layer: relu((x + bias) * scale + shift)
+            const float4 b4 = in_bias ? __ldg(reinterpret_cast<const float4*>(in_bias + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 s4 = in_scale ? __ldg(reinterpret_cast<const float4*>(in_scale + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 t4 = in_scale ? __ldg(reinterpret_cast<const float4*>(in_shift + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (src[q] >= 0) {
+                float4 x = v[h][q];
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                if (in_scale) {
+                  x.x = fmaf(x.x, s4.x, t4.x); x.y = fmaf(x.y, s4.y, t4.y); x.z = fmaf(x.z, s4.z, t4.z); x.w = fmaf(x.w, s4.w, t4.w);
+                }
+                if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                v[h][q] = x;
+              }
+            }
+          }
+          const uint32_t it = seq * (uint32_t)n_kb + (uint32_t)kb;
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          uint8_t* stage = smem_gen + (size_t)s * Cfg::kStageBytes;
+          if (issues_tma) {
+            mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
+            tma_bulk_g2s(smem_base + s * Cfg::kStageBytes + 2 * kABytes,
+                         packed + ((size_t)k * n_kb + kb) * (2 * Cfg::kBBytes / 4), 2 * Cfg::kBBytes, full_bar(s));
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int row = wq * 32 + 4 * q + g;
+            float4 hi, lo;
+            split_tf32(v[h][q].x, hi.x, lo.x);
+            split_tf32(v[h][q].y, hi.y, lo.y);
+            split_tf32(v[h][q].z, hi.z, lo.z);
+            split_tf32(v[h][q].w, hi.w, lo.w);
+            const uint32_t off = sw128_offset(row, c);
+            *reinterpret_cast<float4*>(stage + off) = hi;
+            *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
+          }
+          fence_proxy_async();
+          mbar_arrive(full_bar(s));
+        }
+      }
+    }
+  } else if (warp == kPairMmaWarp) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(kTcTileM, COUT);
+    uint32_t it = 0, seq = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++seq) {
+      const uint32_t buf = seq & 1u;
+      mbar_wait(acc_empty(buf), ((seq >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_d + buf * kAccCols;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_lo + kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int kk = 0; kk < kTcKc / 8; ++kk) {
+            const uint32_t adv = kk * 32;
+            tc_mma_tf32(d_addr, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, accumulate);
+            tc_mma_tf32(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
+            tc_mma_tf32(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
+            accumulate = 1u;
+          }
+          tc_commit(empty_bar(s));
+        }
+        __syncwarp();
+        accumulate = 1u;
+      }
+      if (lane == 0) tc_commit(acc_full(buf));
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> fp32 atomics on the output rows =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    uint32_t seq = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++seq) {
+      const int k = item_k(item);
+      const int first = (item - chunk_prefix[k]) * kTcTileM;
+      const int row = first + quad * 32 + lane;
+      const int o = row < count_s[k] ? __ldg(pair_out + (size_t)k * out_cap + row) : -1;
+      const uint32_t buf = seq & 1u;
+      mbar_wait(acc_full(buf), (seq >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(tmem_d + buf * kAccCols + ((uint32_t)(quad * 32) << 16) + c0, r);
+        if (o >= 0) {
+          float* dst = feat_out + (size_t)o * COUT + c0;
+#pragma unroll
+          for (int q = 0; q < 16; q += 4)
+            red_add_v4(dst + q, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
+                       __uint_as_float(r[q + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kPairMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_rows_kernel(float* __restrict__ feat, const int* __restrict__ n_rows, int row_cap, int channels) {
+  const long long total = (long long)min(*n_rows, row_cap) * channels / 4;
+  float4* p = reinterpret_cast<float4*>(feat);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+    p[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+feature_epilogue_kernel(float* __restrict__ feat, const int* __restrict__ n_rows, int row_cap, int channels,
+                        const float* __restrict__ bias, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ residual, int relu) {
+  const long long total = (long long)min(*n_rows, row_cap) * channels / 4;
+  float4* p = reinterpret_cast<float4*>(feat);
+  const int c4 = channels / 4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(e % c4) * 4;
+    float4 x = p[e];
+    if (bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col)); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+    if (scale) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(scale + col));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(shift + col));
+      x.x = fmaf(x.x, s.x, t.x); x.y = fmaf(x.y, s.y, t.y); x.z = fmaf(x.z, s.z, t.z); x.w = fmaf(x.w, s.w, t.w);
+    }
+    if (residual) { const float4 r = reinterpret_cast<const float4*>(residual)[e]; x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
+    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+    p[e] = x;
+  }
+}
+
 // ---- weight image ------------------------------------------------------------------------
 // packed[k][kb][part][n][swizzled 32 floats], part 0 = hi, 1 = lo; zero beyond c_in.
 __global__ void __launch_bounds__(256)
@@ -372,7 +641,7 @@ pack_weight_kernel(const float* __restrict__ w, int c_in, int c_out, int k_vol, 
 }
 
 static bool tc_shape_ok(int c_in, int c_out) {
-  const bool cin_ok = c_in == 16 || c_in == 32 || c_in == 64 || c_in == 128;
+  const bool cin_ok = c_in >= 4 && c_in <= 128 && c_in % 4 == 0;   // rows are gathered as float4
   const bool cout_ok = c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128;
   return cin_ok && cout_ok;
 }
@@ -396,6 +665,42 @@ static int launch_tc(const float* feat_in, const int32_t* nbr, const uint32_t* t
   return D3B_OK;
 }
 
+template <int COUT>
+static int launch_pairs(const float* feat_in, const int32_t* n_out, int32_t out_cap, const d3b_conv_params* p,
+                        float* feat_out, cudaStream_t stream) {
+  using Cfg = TcCfg<COUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(spconv_pairs_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  zero_rows_kernel<<<grid_for((long long)out_cap * COUT / 4, 256), 256, 0, stream>>>(feat_out, n_out, out_cap, COUT);
+  D3B_LAUNCH_CHECK();
+  const int n_kb = (p->c_in + kTcKc - 1) / kTcKc;
+  spconv_pairs_kernel<COUT><<<kNumSMs, kPairThreads, Cfg::kSmemBytes, stream>>>(
+      feat_in, p->pair_in, p->pair_out, p->pair_count, out_cap, p->k_vol, p->c_in, n_kb, p->weight_packed, p->in_bias,
+      p->in_scale, p->in_shift, p->in_relu, feat_out);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+int sparse_conv_tc_pairs(const float* feat_in, const int32_t* n_out, int32_t out_cap, const d3b_conv_params* p,
+                         float* feat_out, cudaStream_t stream) {
+  if (!tc_shape_ok(p->c_in, p->c_out)) {
+    set_error("pair-based sparse conv: unsupported C_in=%d C_out=%d", p->c_in, p->c_out);
+    return D3B_ERR_UNSUPPORTED;
+  }
+  D3B_REQUIRE(p->weight_packed && p->pair_in && p->pair_out && p->pair_count,
+              "pair-based sparse conv: weight_packed / pair lists missing");
+  D3B_REQUIRE((p->in_scale == nullptr) == (p->in_shift == nullptr), "in_scale and in_shift must be given together");
+  switch (p->c_out) {
+    case 16: return launch_pairs<16>(feat_in, n_out, out_cap, p, feat_out, stream);
+    case 32: return launch_pairs<32>(feat_in, n_out, out_cap, p, feat_out, stream);
+    case 64: return launch_pairs<64>(feat_in, n_out, out_cap, p, feat_out, stream);
+    default: return launch_pairs<128>(feat_in, n_out, out_cap, p, feat_out, stream);
+  }
+}
+
 int sparse_conv_tc(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out,
                    int32_t out_cap, const d3b_conv_params* p, float* feat_out, cudaStream_t stream) {
   if (!tc_shape_ok(p->c_in, p->c_out)) {
@@ -415,6 +720,19 @@ int sparse_conv_tc(const float* feat_in, const int32_t* nbr, const uint32_t* til
 }  // namespace d3b
 
 using namespace d3b;
+
+extern "C" int d3b_feature_epilogue(float* feat, const int32_t* n_rows, int32_t row_cap, int32_t channels,
+                                    const float* bias, const float* scale, const float* shift,
+                                    const float* residual, int32_t relu, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(feat && n_rows && channels >= 4 && channels % 4 == 0 && row_cap >= 0, "d3b_feature_epilogue: bad argument");
+  D3B_REQUIRE((scale == nullptr) == (shift == nullptr), "d3b_feature_epilogue: scale and shift go together");
+  if (row_cap == 0) return D3B_OK;
+  feature_epilogue_kernel<<<grid_for((long long)row_cap * channels / 4, 256), 256, 0, stream>>>(
+      feat, n_rows, row_cap, channels, bias, scale, shift, residual, relu);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
 
 extern "C" size_t d3b_conv_packed_weight_floats(int32_t c_in, int32_t c_out, int32_t k_vol) {
   if (!tc_shape_ok(c_in, c_out) || k_vol < 1 || k_vol > 32) return 0;

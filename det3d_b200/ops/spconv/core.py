@@ -129,6 +129,19 @@ class Rulebook:
         self.stride = stride
         self.padding = padding
         self._ws = None
+        self.pairs = None             # (pair_in [K,cap], pair_out [K,cap], pair_count [K]) once built
+
+
+def build_pairs(rb):
+    """Compact nbr into per-offset (in_row, out_row) lists for the pair-based kernel (buffers reused)."""
+    if rb.pairs is None:
+        dev = rb.nbr.device
+        rb.pairs = (torch.empty_like(rb.nbr), torch.empty_like(rb.nbr), torch.zeros(rb.k_vol, dtype=torch.int32, device=dev))
+    pin, pout, cnt = rb.pairs
+    st = _lib.lib().d3b_rulebook_pairs(rb.nbr.data_ptr(), rb.out_level.n.data_ptr(), rb.out_level.cap, rb.k_vol,
+                                       pin.data_ptr(), pout.data_ptr(), cnt.data_ptr(), _lib.current_stream())
+    _lib.check(st, "d3b_rulebook_pairs")
+    return rb
 
 
 def conv_out_spatial(spatial, ksize, stride, padding):
@@ -201,16 +214,19 @@ class ConvWeights:
         w = weight.detach().to(torch.float32)
         if w.dim() == 5:
             w = w.reshape(-1, w.shape[3], w.shape[4])
+        self.c_in_logical = w.shape[1]
+        if algo is None:
+            algo = default_algo(w.shape[1], w.shape[2])
+        if algo != _lib.ALGO_SIMT and w.shape[1] % 4 != 0:      # tensor-core kernels gather rows as float4
+            w = torch.nn.functional.pad(w, (0, 0, 0, 4 - w.shape[1] % 4))
         self.weight = w.contiguous()
         self.k_vol, self.c_in, self.c_out = self.weight.shape
         f = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
         self.bias, self.scale, self.shift = f(bias), f(scale), f(shift)
         self.relu = bool(relu)
         self.packed = None
-        if algo is None:
-            algo = default_algo(self.c_in, self.c_out)
         self.algo = algo
-        if self.algo == _lib.ALGO_TC:
+        if self.algo != _lib.ALGO_SIMT:
             self._pack()
 
     def _pack(self):
@@ -234,7 +250,8 @@ def force_algo(algo):
 
 
 def tc_supported(c_in, c_out):
-    return _lib.lib().d3b_conv_packed_weight_floats(int(c_in), int(c_out), 27) > 0
+    c_in = (int(c_in) + 3) // 4 * 4      # ConvWeights pads C_in to a multiple of 4 for the tensor-core kernels
+    return _lib.lib().d3b_conv_packed_weight_floats(c_in, int(c_out), 27) > 0
 
 
 def default_algo(c_in, c_out):
@@ -243,8 +260,13 @@ def default_algo(c_in, c_out):
     return _lib.ALGO_TC if tc_supported(c_in, c_out) else _lib.ALGO_SIMT
 
 
-def sparse_conv(feat_in, rb, cw, feat_out, residual=None):
-    """feat_out[:n_out] = epilogue(sum_k feat_in[nbr[k]] @ W[k]).  All device-side."""
+def sparse_conv(feat_in, rb, cw, feat_out, residual=None, in_act=None):
+    """feat_out[:n_out] = epilogue(sum_k feat_in[nbr[k]] @ W[k]).  All device-side.
+
+    With cw.algo == ALGO_TC_PAIRS the kernel writes RAW sums (no bias/BN/ReLU/residual of this layer)
+    and `in_act` = (bias, scale, shift, relu) of the producing layer is applied to the gathered inputs."""
+    if feat_in.shape[1] == cw.c_in_logical and cw.c_in != cw.c_in_logical:
+        feat_in = torch.nn.functional.pad(feat_in, (0, cw.c_in - cw.c_in_logical))
     assert feat_in.dtype == torch.float32 and feat_in.is_contiguous() and feat_in.shape[1] == cw.c_in
     assert feat_out.shape[1] == cw.c_out and feat_out.is_contiguous()
     assert rb.k_vol == cw.k_vol, "kernel volume mismatch"
@@ -259,6 +281,16 @@ def sparse_conv(feat_in, rb, cw, feat_out, residual=None):
     p.residual = _lib.ptr(residual)
     p.relu = 1 if cw.relu else 0
     p.algo = cw.algo
+    if cw.algo == _lib.ALGO_TC_PAIRS:
+        assert residual is None, "the pair-based kernel defers its epilogue: use feature_epilogue for residuals"
+        if rb.pairs is None:
+            build_pairs(rb)
+        p.pair_in, p.pair_out, p.pair_count = (t.data_ptr() for t in rb.pairs)
+        if in_act is not None:
+            b, sc, sh, relu = in_act
+            p.in_bias, p.in_scale, p.in_shift, p.in_relu = _lib.ptr(b), _lib.ptr(sc), _lib.ptr(sh), 1 if relu else 0
+    else:
+        assert in_act is None, "only the pair-based kernel applies a deferred input activation"
     events = PROFILE_EVENTS
     if events is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,6 +304,15 @@ def sparse_conv(feat_in, rb, cw, feat_out, residual=None):
         ev1.record()
         events.append((ev0, ev1))
     return feat_out
+
+
+def feature_epilogue(feat, level, bias=None, scale=None, shift=None, residual=None, relu=False):
+    """In place over the live rows: x = relu?((x + bias) * scale + shift + residual)."""
+    st = _lib.lib().d3b_feature_epilogue(feat.data_ptr(), level.n.data_ptr(), level.cap, feat.shape[1], _lib.ptr(bias),
+                                         _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(residual), 1 if relu else 0,
+                                         _lib.current_stream())
+    _lib.check(st, "d3b_feature_epilogue")
+    return feat
 
 
 def sparse_to_dense(feat, level, out=None):

@@ -11,6 +11,7 @@ all row counts kept on the device.  Buffers are sized once per
 import torch
 from torch import nn
 
+from ... import _lib
 from . import core
 from .modules import SparseConvolution
 
@@ -93,9 +94,12 @@ class FusedSparseEncoder:
             if L.bn is not None:
                 scale, shift = _bn_fold(L.bn)
                 scale, shift = scale.to(device), shift.to(device)
+            algo = self.algo_override
+            if algo is None:   # sparse levels: compacted pairs on the tensor cores whenever the shape allows
+                algo = _lib.ALGO_TC_PAIRS if core.tc_supported(L.conv.in_channels, L.conv.out_channels) else _lib.ALGO_SIMT
             L.cw = core.ConvWeights(
                 L.conv.weight.to(device), bias=None if L.conv.bias is None else L.conv.bias.to(device),
-                scale=scale, shift=shift, relu=L.relu, algo=self.algo_override,
+                scale=scale, shift=shift, relu=L.relu, algo=algo,
             )
             L.sig = sig
 
@@ -177,16 +181,40 @@ class FusedSparseEncoder:
 
         x = feats
         identity = None
+        pending = None   # deferred epilogue (bias, scale, shift, relu) of the layer that produced raw sums in x
+        x_level = lvl0
+
+        def materialize():
+            nonlocal pending
+            if pending is not None:
+                core.feature_epilogue(x, x_level, *pending[:3], relu=pending[3])
+                pending = None
+
         for L, rb, build in st["steps"]:
             if build is not None:
                 build(rb)
+                if L.cw.algo == _lib.ALGO_TC_PAIRS or any(M.cw.algo == _lib.ALGO_TC_PAIRS for M, r2, _b in st["steps"] if r2 is rb):
+                    core.build_pairs(rb)
+            pairs = L.cw.algo == _lib.ALGO_TC_PAIRS
             if L.save_identity:
+                materialize()            # the block input is needed as activated values
                 identity = x
+            if not pairs:
+                materialize()            # output-stationary kernels read activated inputs
             out = self._take(st["pools"], rb.out_level.cap, L.conv.out_channels, (x, identity), device)
-            core.sparse_conv(x, rb, L.cw, out, residual=identity if L.residual else None)
-            if L.residual:
-                identity = None
-            x = out
+            if pairs:
+                core.sparse_conv(x, rb, L.cw, out, in_act=pending)
+                pending = (L.cw.bias, L.cw.scale, L.cw.shift, L.cw.relu)
+                x, x_level = out, rb.out_level
+                if L.residual:
+                    core.feature_epilogue(x, x_level, *pending[:3], residual=identity, relu=pending[3])
+                    pending, identity = None, None
+            else:
+                core.sparse_conv(x, rb, L.cw, out, residual=identity if L.residual else None)
+                if L.residual:
+                    identity = None
+                x, x_level = out, rb.out_level
+        materialize()
         if bev_rows:
             # channels-last [B*H*W, C*D] with channel = c*D + z: same values as dense.view(B, C*D, H, W)
             d, h, w = st["final_level"].spatial

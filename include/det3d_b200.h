@@ -126,8 +126,10 @@ int d3b_rulebook_conv(const int32_t* in_coors, const int32_t* n_in, int32_t in_c
  *    out[o,:] = act( (sum_k in[nbr[k][o],:] . W[k] + bias) * scale + shift
  *                    + residual[o,:] )
  * ========================================================================= */
-#define D3B_ALGO_SIMT 0   /* fp32 FFMA                                      */
-#define D3B_ALGO_TC 1     /* tcgen05 3xTF32 (fp32-equivalent), TMEM accum    */
+#define D3B_ALGO_SIMT 0     /* fp32 FFMA, output-stationary                              */
+#define D3B_ALGO_TC 1       /* tcgen05 3xTF32 (fp32-equivalent), output-stationary tiles  */
+#define D3B_ALGO_TC_PAIRS 2 /* tcgen05 3xTF32 over compacted rulebook pairs (per offset:  */
+                            /* dense chunks of 128 valid pairs), fp32 atomics into feat_out */
 
 typedef struct {
   int32_t c_in, c_out, k_vol;    /* k_vol = kd*kh*kw                          */
@@ -139,7 +141,30 @@ typedef struct {
   const float* residual;         /* [n_out, c_out] or NULL                    */
   int32_t relu;
   int32_t algo;
+  /* D3B_ALGO_TC_PAIRS only -------------------------------------------------- */
+  const int32_t* pair_in;        /* [k_vol, out_cap] input row of pair j of offset k (d3b_rulebook_pairs) */
+  const int32_t* pair_out;       /* [k_vol, out_cap] output row                                           */
+  const int32_t* pair_count;     /* [k_vol] pairs per offset (device)                                      */
+  /* epilogue of the PRODUCER layer, applied to the gathered input rows in registers:
+   *   x = relu?((x + in_bias) * in_scale + in_shift); NULL pointers = identity.
+   * The kernel itself adds raw sums into feat_out (which it zeroes first) and applies
+   * nothing else: bias/scale/shift/residual/relu of THIS layer are the consumer's job
+   * (next conv's in_* fields, or d3b_feature_epilogue). */
+  const float* in_bias;
+  const float* in_scale;
+  const float* in_shift;
+  int32_t in_relu;
 } d3b_conv_params;
+
+/* Compact the output-stationary map into per-offset pair lists (spconv's classic rulebook form):
+ * for every k, the (in_row, out_row) of each valid nbr[k][o], densely packed; pair_count[k] pairs. */
+int d3b_rulebook_pairs(const int32_t* nbr, const int32_t* n_out, int32_t out_cap, int32_t k_vol,
+                       int32_t* pair_in, int32_t* pair_out, int32_t* pair_count, void* stream);
+
+/* In-place epilogue over rows [0, *n_rows): x = relu?((x + bias) * scale + shift + residual). */
+int d3b_feature_epilogue(float* feat, const int32_t* n_rows, int32_t row_cap, int32_t channels,
+                         const float* bias, const float* scale, const float* shift,
+                         const float* residual, int32_t relu, void* stream);
 
 /* Size in floats / fill of the tensor-core weight image (hi/lo TF32 split,
  * K-major 128B-swizzled tiles).  Done once per layer at model load. */

@@ -119,7 +119,8 @@ def test_fused_bev_path_matches_cudnn_path(setup):
         with torch.no_grad():
             rows, (b, h, w) = model.backbone.forward_rows(vox["mean"], vox["coors"], 1, grid, n_dev=vox["counts"][1:2])
             dense = model.backbone(vox["mean"], vox["coors"], 1, grid, n_dev=vox["counts"][1:2])
-            assert torch.equal(rows.view(b, h, w, -1).permute(0, 3, 1, 2), dense)
+            # same values in the two layouts (the pair-based encoder sums with fp32 atomics: not bit-stable run to run)
+            assert torch.allclose(rows.view(b, h, w, -1).permute(0, 3, 1, 2), dense, rtol=1e-5, atol=1e-5 * float(dense.abs().max()))
             fused = model.fused_bev().run(rows, b, h, w)
             ref = model.bbox_head(model.neck(dense))
     finally:
@@ -151,16 +152,19 @@ def test_cbgs_nuscenes_config_batch2():
     pts = torch.from_numpy(np.concatenate(clouds)).cuda()
     offsets = [0, 35000, 70000]
     det = pipe.forward_device(pts, offsets)
-    assert det["boxes"].shape == (2, 6 * 83, 9)
-    got = pipe.unpack(pipe.pack(det).cpu())
+    assert det["boxes"].shape == (2, 6 * 83, 9) and int(det["valid"].sum()) > 20
 
-    # same head outputs -> CPU restatement of predict
+    # one set of head outputs -> device predict vs the CPU restatement of predict.  (The encoder is not
+    # re-run for the comparison: its pair-based layers sum with fp32 atomics, so two runs differ in the
+    # last bits and near-tied random-weight scores may reorder.)
     with torch.no_grad():
         vox = pipe.voxelizer(pts, offsets)
         counts = vox["counts"].cpu().numpy()
         assert counts[2] == counts[0] + counts[1] and counts[0] > 10000
         x = model.backbone(vox["mean"], vox["coors"], 2, [int(g) for g in pipe.grid_size], n_dev=vox["counts"][2:3])
         preds = model.bbox_head(model.neck(x))
+        det2 = model.bbox_head.predict_device(dict(anchors=pipe.anchors(2)), preds, cfg.test_cfg)
+    got = pipe.unpack(pipe.pack(det2).cpu())
     flag = 0
     want = [dict(b=[], s=[], l=[]) for _ in range(2)]
     for task_id, p in enumerate(preds):
