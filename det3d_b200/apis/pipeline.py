@@ -26,8 +26,11 @@ class InferencePipeline:
             model = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
         self.model = model.to(self.device).eval()
         vg = cfg.voxel_generator
+        # VoxelFeatureExtractorV3 only needs the per-voxel mean (fused into the voxelizer); the pillar reader
+        # consumes the point slots themselves
+        self._reader_takes_points = cfg.model["reader"]["type"] != "VoxelFeatureExtractorV3"
         self.voxelizer = Voxelizer(vg["voxel_size"], vg["range"], vg["max_points_in_voxel"], vg["max_voxel_num"],
-                                   want_voxels=False, want_mean=True)
+                                   want_voxels=self._reader_takes_points, want_mean=not self._reader_takes_points)
         self.grid_size = self.voxelizer.grid_size
         self.num_point_features = int(cfg.model["reader"].get("num_input_features", 4))
         out_size_factor = cfg.assigner["out_size_factor"] if "assigner" in cfg else 8
@@ -49,7 +52,7 @@ class InferencePipeline:
         batch = len(offsets) - 1
         vox = self.voxelizer(points, offsets)
         example = dict(
-            voxels=vox["mean"], coordinates=vox["coors"], num_points=vox["num_points"],
+            voxels=vox["voxels"] if self._reader_takes_points else vox["mean"], coordinates=vox["coors"], num_points=vox["num_points"],
             num_voxels=[None] * batch, shape=[self.grid_size], anchors=self.anchors(batch),
             n_voxels_dev=vox["counts"][batch:batch + 1],
         )

@@ -22,7 +22,7 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 }  // namespace d3b
 
 extern "C" const char* d3b_last_error(void) { return d3b::g_error; }
-extern "C" int d3b_abi_version(void) { return 1; }
+extern "C" int d3b_abi_version(void) { return 2; }
 extern "C" unsigned long long d3b_launch_count(void) {
   return d3b::g_launches.load(std::memory_order_relaxed);
 }

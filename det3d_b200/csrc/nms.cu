@@ -437,11 +437,19 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
     if (threadIdx.x == 0) {
       unsigned long long cur = remv[b], kept = 0ULL;
       int total = kept_total;
-      for (int i = 0; i < in_block && total < max_keep; ++i) {
-        if (!((cur >> i) & 1ULL)) {
-          kept |= 1ULL << i;
-          cur |= diag[i];
-          keep_idx[total++] = (long long)b * kNmsBlock + i;
+      // the diag loads do not depend on `cur`: fetch them eight at a time so the serial chain is ALU-only
+      for (int i0 = 0; i0 < in_block && total < max_keep; i0 += 8) {
+        unsigned long long d8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d8[u] = diag[(i0 + u) & (kNmsBlock - 1)];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u;
+          if (i < in_block && total < max_keep && !((cur >> i) & 1ULL)) {
+            kept |= 1ULL << i;
+            cur |= d8[u];
+            keep_idx[total++] = (long long)b * kNmsBlock + i;
+          }
         }
       }
       kept_word = kept;

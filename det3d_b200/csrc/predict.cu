@@ -73,9 +73,17 @@ topk_select_kernel(const float* __restrict__ values, int A, int k, float* __rest
     __syncthreads();
     const unsigned int prefix = s_prefix;
     const unsigned int pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    for (int i = tid; i < A; i += kTopkThreads) {
-      const unsigned int key = float_to_ordered(v[i]);
-      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    // warp-aggregated histogram: detector logits share their leading bits, so per-element shared-memory
+    // atomics would all land on one or two bins and serialise
+    const int a_pad = (A + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
+    for (int i = tid; i < a_pad; i += kTopkThreads) {
+      int digit = -1 - lane;                                   // inactive lanes get unique keys
+      if (i < A) {
+        const unsigned int key = float_to_ordered(v[i]);
+        if ((key & pmask) == prefix) digit = (int)((key >> shift) & 255u);
+      }
+      const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+      if (digit >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
     }
     __syncthreads();
     if (tid == 0) {

@@ -1,1 +1,2 @@
+from .point_pillars import PointPillars
 from .voxelnet import SingleStageDetector, VoxelNet

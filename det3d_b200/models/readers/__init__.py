@@ -1,1 +1,2 @@
+from .pillar_encoder import PFNLayer, PillarFeatureNet, PointPillarsScatter
 from .voxel_encoder import VoxelFeatureExtractorV3

@@ -164,11 +164,21 @@ def alloc_subm_rulebook(level, ksize):
     return Rulebook(nbr, tile_mask, ksize, level, level, "subm")
 
 
-def build_subm_rulebook(rb):
+def _pair_ptrs(rb, with_pairs):
+    if not with_pairs:
+        return None, None, None
+    if rb.pairs is None:
+        dev = rb.nbr.device
+        rb.pairs = (torch.empty_like(rb.nbr), torch.empty_like(rb.nbr), torch.zeros(rb.k_vol, dtype=torch.int32, device=dev))
+    return tuple(t.data_ptr() for t in rb.pairs)
+
+
+def build_subm_rulebook(rb, with_pairs=False):
     level = rb.out_level
+    pin, pout, pcnt = _pair_ptrs(rb, with_pairs)
     st = _lib.lib().d3b_rulebook_subm(
         level.coors.data_ptr(), level.n.data_ptr(), level.cap, C.byref(level.index), _i3(rb.ksize),
-        rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), _lib.current_stream(),
+        rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), pin, pout, pcnt, _lib.current_stream(),
     )
     _lib.check(st, "d3b_rulebook_subm")
     return rb
@@ -194,12 +204,13 @@ def alloc_conv_rulebook(in_level, ksize, stride, padding, out_cap=None):
     return rb
 
 
-def build_conv_rulebook(rb):
+def build_conv_rulebook(rb, with_pairs=False):
     i, o = rb.in_level, rb.out_level
+    pin, pout, pcnt = _pair_ptrs(rb, with_pairs)
     st = _lib.lib().d3b_rulebook_conv(
         i.coors.data_ptr(), i.n.data_ptr(), i.cap, C.byref(i.index), _i3(rb.ksize), _i3(rb.stride),
         _i3(rb.padding), C.byref(o.index), o.coors.data_ptr(), o.n.data_ptr(), o.cap,
-        rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), rb._ws.data_ptr(), rb._ws.numel(),
+        rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), pin, pout, pcnt, rb._ws.data_ptr(), rb._ws.numel(),
         _lib.current_stream(),
     )
     _lib.check(st, "d3b_rulebook_conv")

@@ -191,10 +191,8 @@ class FusedSparseEncoder:
                 pending = None
 
         for L, rb, build in st["steps"]:
-            if build is not None:
-                build(rb)
-                if L.cw.algo == _lib.ALGO_TC_PAIRS or any(M.cw.algo == _lib.ALGO_TC_PAIRS for M, r2, _b in st["steps"] if r2 is rb):
-                    core.build_pairs(rb)
+            if build is not None:   # pairs are compacted inside the neighbour kernel when any user of this rulebook needs them
+                build(rb, with_pairs=any(M.cw.algo == _lib.ALGO_TC_PAIRS for M, r2, _b in st["steps"] if r2 is rb))
             pairs = L.cw.algo == _lib.ALGO_TC_PAIRS
             if L.save_identity:
                 materialize()            # the block input is needed as activated values

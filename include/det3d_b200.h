@@ -102,10 +102,13 @@ size_t d3b_rulebook_workspace_bytes(int64_t n_words);
 int d3b_index_build_hash(const int32_t* coors, const int32_t* n_rows, int32_t row_cap,
                          d3b_site_index* index, void* stream);
 
-/* Submanifold rulebook: outputs == inputs (same rows, same order). */
+/* Submanifold rulebook: outputs == inputs (same rows, same order).
+ * pair_in / pair_out [k_vol, row_cap] + pair_count [k_vol] (all three or none, may be NULL): the same
+ * map additionally compacted per offset into (in_row, out_row) lists for D3B_ALGO_TC_PAIRS. */
 int d3b_rulebook_subm(const int32_t* coors, const int32_t* n_rows, int32_t row_cap,
                       const d3b_site_index* index, const int32_t ksize[3],
-                      int32_t* nbr, uint32_t* tile_mask, void* stream);
+                      int32_t* nbr, uint32_t* tile_mask, int32_t* pair_in, int32_t* pair_out,
+                      int32_t* pair_count, void* stream);
 
 /* Strided sparse conv rulebook.  Output sites = every site reachable from an
  * active input, in ascending linear index ((b*D+z)*H+y)*W+x.  Fills
@@ -114,7 +117,8 @@ int d3b_rulebook_conv(const int32_t* in_coors, const int32_t* n_in, int32_t in_c
                       const d3b_site_index* in_index, const int32_t ksize[3],
                       const int32_t stride[3], const int32_t padding[3],
                       d3b_site_index* out_index, int32_t* out_coors, int32_t* n_out,
-                      int32_t out_cap, int32_t* nbr, uint32_t* tile_mask, void* workspace,
+                      int32_t out_cap, int32_t* nbr, uint32_t* tile_mask, int32_t* pair_in,
+                      int32_t* pair_out, int32_t* pair_count, void* workspace,
                       size_t workspace_bytes, void* stream);
 
 /* ========================================================================= *
@@ -175,6 +179,19 @@ int d3b_conv_pack_weight(const float* weight_dev, int32_t c_in, int32_t c_out, i
 int d3b_sparse_conv(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask,
                     const int32_t* n_out, int32_t out_cap, const d3b_conv_params* p,
                     float* feat_out, void* stream);
+
+/* PillarFeatureNet, eval mode, one PFN layer (every Det3D PointPillars config): decoration
+ * (x,y,z,.. | xyz - pillar mean | xy - pillar centre), Linear(ndim+5 -> units, no bias), BatchNorm1d folded
+ * to scale/shift, ReLU, max over the max_points slots -- padded slots count as all-zero features, as the
+ * reference's mask makes them.  replaces det3d/models/readers/pillar_encoder.py:115-155 (+ PFNLayer :33-47).
+ * voxels [row_cap, max_points, ndim] f32, num_points [row_cap] i32, coors [row_cap, 4] i32 (b,z,y,x),
+ * n_rows device i32 (live rows; the rest of `out` is zero-filled), weight [units, ndim+5] (nn.Linear
+ * layout), out [row_cap, units].  x_offset = vx/2 + range_min_x (likewise y).
+ * D3B_ERR_UNSUPPORTED unless 3 <= ndim <= 11 and units in {32, 64, 96, 128}. */
+int d3b_pillar_features(const float* voxels, const int32_t* num_points, const int32_t* coors,
+                        const int32_t* n_rows, int32_t row_cap, int32_t max_points, int32_t ndim,
+                        int32_t units, const float* weight, const float* scale, const float* shift,
+                        float vx, float vy, float x_offset, float y_offset, float* out, void* stream);
 
 /* .dense(): rows -> zero-initialised [B, C, D, H, W] (caller zero-fills `out`).
  * replaces SparseConvTensor.dense() at scn.py:192,365. */

@@ -29,7 +29,7 @@ def test_binding_table_covers_the_header():
 
 def test_version_and_error_string():
     L = _lib.lib()
-    assert L.d3b_abi_version() == 1
+    assert L.d3b_abi_version() == 2
     assert isinstance(L.d3b_last_error(), bytes)
     assert L.d3b_launch_count() >= 0
 

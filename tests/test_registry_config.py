@@ -65,6 +65,7 @@ def test_shipped_config_builds_second():
 @pytest.mark.parametrize("rel", [
     "examples/second/configs/kitti_car_vfev3_spmiddlefhd_rpn1_mghead_syncbn.py",
     "examples/cbgs/configs/nusc_all_vfev3_spmiddleresnetfhd_rpn2_mghead_syncbn.py",
+    "examples/point_pillars/configs/kitti_point_pillars_mghead_syncbn.py",
 ])
 def test_reference_config_loads_unchanged(rel):
     from det3d.models import build_detector
@@ -72,6 +73,18 @@ def test_reference_config_loads_unchanged(rel):
 
     cfg = Config.fromfile(os.path.join(REFERENCE, rel))
     model = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+    if "point_pillars" in rel:
+        assert type(model).__name__ == "PointPillars"
+        mine = Config.fromfile(os.path.join(ROOT, "configs", "pointpillars_kitti_car.py"))
+        m2 = build_detector(mine.model, train_cfg=None, test_cfg=mine.test_cfg)
+        a, b = model.state_dict(), m2.state_dict()
+        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+        assert tuple(a["reader.pfn_layers.0.linear.weight"].shape) == (64, 9)
+        assert tuple(a["neck.deblocks.2.0.weight"].shape) == (256, 128, 4, 4)
+        for key in ("test_cfg", "voxel_generator", "target_assigner"):
+            assert cfg[key].to_dict() == mine[key].to_dict()
+        assert cfg.assigner.out_size_factor == 2
+        return
     assert type(model).__name__ == "VoxelNet"
     if "kitti_car" in rel:
         mine = Config.fromfile(os.path.join(ROOT, "configs", "second_kitti_car.py"))
