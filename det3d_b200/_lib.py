@@ -14,6 +14,7 @@ D3B_OK = 0
 ALGO_SIMT = 0
 ALGO_TC = 1
 ALGO_TC_PAIRS = 2
+AA_IOU3D, AA_PIXEL = 0, 1
 BOX_XYXYR = 0
 BOX_XYWLR = 1
 
@@ -113,7 +114,7 @@ SIGNATURES = {
     "d3b_boxes_iou_bev": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "d3b_nms_workspace_bytes": (_sz, [_i32]),
     "d3b_rotate_nms": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "d3b_normal_nms": (C.c_int, [_vp, _i32, _vp, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "d3b_normal_nms": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -97,11 +97,12 @@ def rotate_nms(rbboxes, scores, pre_max_size=None, post_max_size=None, iou_thres
 
 
 def nms(bboxes, scores, pre_max_size=None, post_max_size=None, iou_threshold=0.5):
-    """bboxes [N,4] (x1, y1, x2, y2) axis-aligned."""
+    """bboxes [N,4] (x1, y1, x2, y2) axis-aligned; the "+1" pixel IoU of the numba nms_gpu the reference calls
+    here (box_torch_ops.py:506-525 -> ops/nms/nms_gpu.py:22-33,129-166)."""
     bboxes, scores, indices = _topk_prefix(bboxes, scores, pre_max_size)
     if bboxes.shape[0] == 0:
         return torch.zeros([0], dtype=torch.long, device=bboxes.device)
-    keep = nms_ops.normal_nms_xyxy(bboxes, scores, iou_threshold, post_max_size)
+    keep = nms_ops.normal_nms_xyxy(bboxes, scores, iou_threshold, post_max_size, pixel=True)
     if keep.shape[0] == 0:
         return torch.zeros([0], dtype=torch.long, device=bboxes.device)
     return keep if indices is None else indices[keep]

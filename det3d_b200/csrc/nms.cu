@@ -184,6 +184,20 @@ __device__ __forceinline__ float iou_axis_aligned(const float* a, const float* b
   return inter / fmaxf(sa + sb - inter, kEps);
 }
 
+// numba nms_gpu.py:22-33 (`iou_device`, the IoU behind box_torch_ops.nms): +1 "pixel" extents.  Under numba's
+// typing the float32 differences are promoted to float64 by the integer literal, so everything after the
+// fp32 subtraction is double arithmetic; the result is compared against the float32 threshold in double.
+__device__ __forceinline__ double iou_pixel(const float* a, const float* b) {
+  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  const double width = fmax((double)__fsub_rn(right, left) + 1.0, 0.0);
+  const double height = fmax((double)__fsub_rn(bottom, top) + 1.0, 0.0);
+  const double inter = width * height;
+  const double sa = ((double)__fsub_rn(a[2], a[0]) + 1.0) * ((double)__fsub_rn(a[3], a[1]) + 1.0);
+  const double sb = ((double)__fsub_rn(b[2], b[0]) + 1.0) * ((double)__fsub_rn(b[3], b[1]) + 1.0);
+  return inter / (sa + sb - inter);
+}
+
 // Exact-safe rejection: when the circumscribed circles (about the rectangle
 // centres, the rotation pivots) are separated by more than a 1e-3 cushion the
 // reference routine finds no intersection point and no contained corner
@@ -333,7 +347,7 @@ pair_matrix_kernel(int na, const float* __restrict__ boxes_a, int nb, const floa
 constexpr int kNmsRowsPerCta = 16;
 constexpr int kNmsSlices = kNmsBlock / kNmsRowsPerCta;
 
-template <int FMT>  // 0 xyxyr rotated, 1 xywlr rotated, 2 axis-aligned (xyxyr boxes, angle ignored)
+template <int FMT>  // 0 xyxyr rotated, 1 xywlr rotated, 2 axis-aligned (xyxyr boxes, angle ignored), 3 axis-aligned "+1"
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restrict__ n_dev, float thresh,
                 int col_blocks, unsigned long long* __restrict__ mask) {
@@ -391,8 +405,10 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
           if (!(thresh >= 0.0f && surely_disjoint(dc, dcol[tx]))) bit = iou_xyxyr(cur_box, scol + tx * 5) > thresh;
         } else if (FMT == 1) {
           bit = suppresses_xywlr(qrow[rr], qcol[tx], thresh, nullptr);
-        } else {
+        } else if (FMT == 2) {
           bit = iou_axis_aligned(cur_box, scol + tx * 5) > thresh;
+        } else {
+          bit = iou_pixel(cur_box, scol + tx * 5) > (double)thresh;
         }
       }
       const unsigned int word = __ballot_sync(0xffffffffu, bit);
@@ -492,8 +508,10 @@ static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* 
     nms_mask_kernel<0><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   else if (fmt_kernel == 1)
     nms_mask_kernel<1><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
-  else
+  else if (fmt_kernel == 2)
     nms_mask_kernel<2><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+  else
+    nms_mask_kernel<3><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   D3B_LAUNCH_CHECK();
   size_t smem = (size_t)col_blocks * 8;
   if (smem > 200 * 1024) {
@@ -553,16 +571,17 @@ extern "C" int d3b_rotate_nms(const float* boxes, int32_t n_cap, const int32_t* 
                     (long long*)keep_idx, keep_count, workspace, workspace_bytes, stream);
 }
 
-extern "C" int d3b_normal_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev, float thresh,
-                              int32_t max_keep, int64_t* keep_idx, int32_t* keep_count, void* workspace,
+extern "C" int d3b_normal_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev, int32_t mode,
+                              float thresh, int32_t max_keep, int64_t* keep_idx, int32_t* keep_count, void* workspace,
                               size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   D3B_REQUIRE(n_cap >= 0 && max_keep >= 0 && keep_count, "d3b_normal_nms: bad argument");
+  D3B_REQUIRE(mode == D3B_AA_IOU3D || mode == D3B_AA_PIXEL, "d3b_normal_nms: unknown mode %d", mode);
   if (n_cap == 0 || max_keep == 0) {
     D3B_CUDA(cudaMemsetAsync(keep_count, 0, 4, stream));
     return D3B_OK;
   }
   D3B_REQUIRE(boxes && keep_idx && workspace, "d3b_normal_nms: null argument");
-  return nms_common(2, boxes, n_cap, n_boxes_dev, thresh, max_keep, (long long*)keep_idx, keep_count,
-                    workspace, workspace_bytes, stream);
+  return nms_common(mode == D3B_AA_PIXEL ? 3 : 2, boxes, n_cap, n_boxes_dev, thresh, max_keep, (long long*)keep_idx,
+                    keep_count, workspace, workspace_bytes, stream);
 }

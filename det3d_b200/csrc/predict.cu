@@ -77,7 +77,7 @@ topk_select_kernel(const float* __restrict__ values, int A, int k, float* __rest
     // atomics would all land on one or two bins and serialise
     const int a_pad = (A + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
     for (int i = tid; i < a_pad; i += kTopkThreads) {
-      int digit = -1 - lane;                                   // inactive lanes get unique keys
+      int digit = -1;   // lanes outside the prefix share one tag (a single match group, no atomic)
       if (i < A) {
         const unsigned int key = float_to_ordered(v[i]);
         if ((key & pmask) == prefix) digit = (int)((key >> shift) & 255u);
@@ -358,7 +358,8 @@ extern "C" int d3b_predict_task(const d3b_predict_params* q, float* packed, int3
                           (int64_t*)(w.keep_idx + (size_t)b * q->post_max), w.keep_count + b, w.nms_ws,
                           w.nms_ws_bytes, stream);
     else
-      st = d3b_normal_nms(boxes, q->pre_max, w.n_valid + b, q->nms_iou_threshold, q->post_max,
+      st = d3b_normal_nms(boxes, q->pre_max, w.n_valid + b, D3B_AA_PIXEL /* box_torch_ops.nms, mg_head.py:1013-1017 */,
+                          q->nms_iou_threshold, q->post_max,
                           (int64_t*)(w.keep_idx + (size_t)b * q->post_max), w.keep_count + b, w.nms_ws,
                           w.nms_ws_bytes, stream);
     if (st != D3B_OK) return st;

@@ -131,7 +131,7 @@ rb_neighbours(const int* __restrict__ out_coors, const int* __restrict__ n_out, 
       // classic rulebook form for the pair-based kernel: the warp's valid entries of one offset take
       // consecutive slots through one aggregated atomicAdd (pair order inside an offset is arbitrary)
       const int lane = threadIdx.x & 31;
-      const unsigned int grp = __match_any_sync(__activemask(), r >= 0 ? k : -1 - lane);
+      const unsigned int grp = __match_any_sync(__activemask(), r >= 0 ? k : -1);   // misses share one tag
       if (r >= 0) {
         const int leader = __ffs(grp) - 1;
         int base = 0;
@@ -328,7 +328,7 @@ rb_compact_pairs(const int* __restrict__ nbr, const int* __restrict__ n_out, int
       src = nbr[(size_t)k * out_cap + o];
     }
     const bool valid = src >= 0;
-    const unsigned int peers = __match_any_sync(0xffffffffu, valid ? k : -1 - (int)(threadIdx.x & 31));
+    const unsigned int peers = __match_any_sync(0xffffffffu, valid ? k : -1);
     if (valid) {
       const int leader = __ffs(peers) - 1;
       int base = 0;

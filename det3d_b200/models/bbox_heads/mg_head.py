@@ -155,7 +155,8 @@ class MultiGroupHead(nn.Module):
                 bb = torch.cat([box_torch_ops.corner_to_standup_nd(corners),
                                 torch.zeros((pre, 1), device=dev)], dim=1).contiguous()
                 keep_idx, keep_count = nms_ops.nms_sorted(bb, _lib.BOX_XYXYR, float(nms_cfg["nms_iou_threshold"]),
-                                                          post, n_dev=n_valid[b:b + 1], axis_aligned=True)
+                                                          post, n_dev=n_valid[b:b + 1], axis_aligned=True,
+                                                          aa_mode=_lib.AA_PIXEL)
             ok = slot < keep_count.to(torch.long)
             keep_all.append(torch.where(ok, keep_idx[:post], torch.zeros_like(keep_idx[:post])))
             ok_all.append(ok)

@@ -85,7 +85,9 @@ class PillarFeatureNet(nn.Module):
         shift = (bn.bias.double() - bn.running_mean.double() * bn.weight.double() / torch.sqrt(var + bn.eps)).float().contiguous()
         w = layer.linear.weight.detach().float().contiguous()          # [units, ndim + 5]
         m, p, ndim = features.shape
-        out = torch.empty((max(m, 1), layer.units), dtype=torch.float32, device=features.device)
+        if m == 0:
+            return features.new_zeros((0, layer.units))
+        out = torch.empty((m, layer.units), dtype=torch.float32, device=features.device)
         if n_dev is None:
             n_dev = torch.tensor([m], dtype=torch.int32, device=features.device)
         st = _lib.lib().d3b_pillar_features(

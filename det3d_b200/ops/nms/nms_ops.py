@@ -14,7 +14,8 @@ def _workspace(n, device):
     return ws
 
 
-def nms_sorted(boxes_sorted, fmt, thresh, max_keep=None, n_dev=None, axis_aligned=False, out=None):
+def nms_sorted(boxes_sorted, fmt, thresh, max_keep=None, n_dev=None, axis_aligned=False, out=None,
+               aa_mode=_lib.AA_IOU3D):
     """Greedy NMS over boxes already sorted by descending score ([N,5] f32 cuda).
 
     Returns (keep_idx int64[max_keep], keep_count int32[1]) device tensors -- no host sync.
@@ -32,7 +33,7 @@ def nms_sorted(boxes_sorted, fmt, thresh, max_keep=None, n_dev=None, axis_aligne
     ws = _workspace(n, dev)
     L = _lib.lib()
     if axis_aligned:
-        st = L.d3b_normal_nms(boxes_sorted.data_ptr(), n, _lib.ptr(n_dev), float(thresh), max_keep,
+        st = L.d3b_normal_nms(boxes_sorted.data_ptr(), n, _lib.ptr(n_dev), int(aa_mode), float(thresh), max_keep,
                               keep_idx.data_ptr(), keep_count.data_ptr(), ws.data_ptr(), ws.numel(),
                               _lib.current_stream())
     else:
@@ -56,11 +57,13 @@ def rotate_nms_xywlr(rbboxes, scores, iou_threshold, post_max_size=None):
     return _finish(order, keep_idx, keep_count)
 
 
-def normal_nms_xyxy(bboxes, scores, iou_threshold, post_max_size=None):
-    """[N,4] (x1,y1,x2,y2) axis-aligned NMS (iou3d nms_normal semantics, `>`)."""
+def normal_nms_xyxy(bboxes, scores, iou_threshold, post_max_size=None, pixel=False):
+    """[N,4] (x1,y1,x2,y2) axis-aligned NMS, `>`.  pixel=False: iou3d nms_normal extents;
+    pixel=True: the "+1" extents of numba nms_gpu (what box_torch_ops.nms calls, nms_gpu.py:22-33)."""
     order = torch.argsort(scores, descending=True, stable=True)
     b5 = torch.cat([bboxes.float(), bboxes.new_zeros((bboxes.shape[0], 1), dtype=torch.float32)], dim=1)
-    keep_idx, keep_count = nms_sorted(b5[order], _lib.BOX_XYXYR, iou_threshold, post_max_size, axis_aligned=True)
+    keep_idx, keep_count = nms_sorted(b5[order], _lib.BOX_XYXYR, iou_threshold, post_max_size, axis_aligned=True,
+                                      aa_mode=_lib.AA_PIXEL if pixel else _lib.AA_IOU3D)
     return _finish(order, keep_idx, keep_count)
 
 

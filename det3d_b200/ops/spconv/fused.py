@@ -78,6 +78,7 @@ class FusedSparseEncoder:
         self.plan = compile_plan(middle_conv)
         self._state = None
         self.algo_override = None  # testing hook: force SIMT / TC for every layer
+        self.overlap_rulebooks = True   # build the rulebook chain on a side stream (see run)
 
     # ---- parameters ------------------------------------------------------------
     def _refresh_weights(self, device):
@@ -140,6 +141,10 @@ class FusedSparseEncoder:
         return st
 
     @staticmethod
+    def _wants_pairs(st, rb):
+        return any(M.cw.algo == _lib.ALGO_TC_PAIRS for M, r2, _b in st["steps"] if r2 is rb)
+
+    @staticmethod
     def _take(pools, cap, c, busy, device):
         pool = pools[(cap, c)]
         for t in pool:
@@ -190,9 +195,32 @@ class FusedSparseEncoder:
                 core.feature_epilogue(x, x_level, *pending[:3], relu=pending[3])
                 pending = None
 
+        # Rulebooks depend on coordinates only: build the whole chain (level 0 .. 3) on a side stream while the
+        # main stream runs the convolutions of the levels already indexed.  Fork / join through events, so the
+        # overlap is preserved as parallel branches when the forward is captured into a CUDA graph.
+        main = torch.cuda.current_stream(device)
+        ready = {}
+        builds = [(rb, build) for _L, rb, build in st["steps"] if build is not None]
+        if self.overlap_rulebooks and len(builds) > 1:
+            side = st.get("side_stream")
+            if side is None:
+                side = st["side_stream"] = torch.cuda.Stream(device=device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for rb, build in builds:
+                    build(rb, with_pairs=self._wants_pairs(st, rb))
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    ready[id(rb)] = ev
+            builds = []
+        waited = set()
+
         for L, rb, build in st["steps"]:
-            if build is not None:   # pairs are compacted inside the neighbour kernel when any user of this rulebook needs them
-                build(rb, with_pairs=any(M.cw.algo == _lib.ALGO_TC_PAIRS for M, r2, _b in st["steps"] if r2 is rb))
+            if build is not None and builds:   # single-stream order: pairs are compacted inside the neighbour kernel
+                build(rb, with_pairs=self._wants_pairs(st, rb))
+            if id(rb) in ready and id(rb) not in waited:
+                main.wait_event(ready[id(rb)])
+                waited.add(id(rb))
             pairs = L.cw.algo == _lib.ALGO_TC_PAIRS
             if L.save_identity:
                 materialize()            # the block input is needed as activated values

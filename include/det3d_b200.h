@@ -237,8 +237,13 @@ int d3b_rotate_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev
                    float thresh, int32_t max_keep, int64_t* keep_idx, int32_t* keep_count,
                    void* workspace, size_t workspace_bytes, void* stream);
 
-/* Axis-aligned variant. replaces nms_normal_gpu, iou3d.cpp:123-170. */
-int d3b_normal_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev, float thresh,
+/* Axis-aligned variants, boxes [n,5] = (x1, y1, x2, y2, ignored), suppress when iou > thresh.
+ * mode = D3B_AA_IOU3D: plain extents       -- nms_normal_gpu, iou3d.cpp:123-170 / iou3d_kernel.cu:295-303
+ * mode = D3B_AA_PIXEL: "+1" pixel extents  -- numba nms_gpu behind box_torch_ops.nms
+ *                      (det3d/ops/nms/nms_gpu.py:22-33,129-166, core/bbox/box_torch_ops.py:506-525) */
+#define D3B_AA_IOU3D 0
+#define D3B_AA_PIXEL 1
+int d3b_normal_nms(const float* boxes, int32_t n_cap, const int32_t* n_boxes_dev, int32_t mode, float thresh,
                    int32_t max_keep, int64_t* keep_idx, int32_t* keep_count, void* workspace,
                    size_t workspace_bytes, void* stream);
 

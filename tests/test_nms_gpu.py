@@ -158,3 +158,21 @@ def test_axis_aligned_nms_api():
     b = torch.tensor([[0, 0, 2, 2], [0.1, 0, 2.1, 2], [5, 5, 7, 7.0]], device="cuda")
     s = torch.tensor([0.5, 0.9, 0.7], device="cuda")
     assert box_torch_ops.nms(b, s, None, None, 0.5).tolist() == [1, 2]
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.5, 0.7])
+def test_box_torch_ops_nms_pixel_matches_reference_golden(thr):
+    """a14: box_torch_ops.nms = numba nms_gpu semantics ("+1" extents, float64 after the fp32 differences)."""
+    from conftest import load_golden
+    from det3d.core.bbox import box_torch_ops
+    g = load_golden("aa_nms_pixel_700")
+    dets = torch.from_numpy(g["dets"]).cuda()
+    keep = box_torch_ops.nms(dets[:, :4], dets[:, 4], iou_threshold=thr)
+    assert keep.dtype == torch.int64 and keep.is_cuda
+    assert np.array_equal(keep.cpu().numpy(), g["keep_t%02d" % int(thr * 100)])                # bit-exact keep list
+    k2 = box_torch_ops.nms(dets[:, :4], dets[:, 4], pre_max_size=300, post_max_size=50, iou_threshold=thr)
+    from oracle.aa_nms import nms_pixel
+    top = np.argsort(-g["dets"][:, 4], kind="stable")[:300]
+    want = top[nms_pixel(g["dets"][top], thr)][:50]
+    assert np.array_equal(k2.cpu().numpy(), want)
+    assert box_torch_ops.nms(dets[:0, :4], dets[:0, 4]).shape == (0,)

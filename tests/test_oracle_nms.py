@@ -83,3 +83,14 @@ def test_rotate_nms_cc_threshold_is_inclusive():
     # touching boxes (zero overlap) are never suppressed even at thresh 0: the hull test skips them
     dets = np.array([[0, 0, 2, 2, 0, 0.9], [2, 0, 2, 2, 0, 0.8]], np.float32)
     assert rotate_nms_cc(dets, 0.0).tolist() == [0, 1]
+
+
+def test_axis_aligned_pixel_nms_oracle_matches_reference_golden():
+    """a14: the "+1" IoU of numba nms_gpu; golden = the reference's own source compiled for the CPU target."""
+    from conftest import load_golden
+    from oracle.aa_nms import iou_pixel_matrix, nms_pixel
+    g = load_golden("aa_nms_pixel_700")
+    iou = iou_pixel_matrix(g["dets"][:, :4])
+    assert np.array_equal(iou[g["pair_idx"][:, 0], g["pair_idx"][:, 1]], g["pair_iou"])      # bit-exact float64
+    for thr in (0.3, 0.5, 0.7):
+        assert np.array_equal(nms_pixel(g["dets"], thr), g["keep_t%02d" % int(thr * 100)])
