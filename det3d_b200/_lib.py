@@ -17,6 +17,7 @@ ALGO_TC_PAIRS = 2
 AA_IOU3D, AA_PIXEL = 0, 1
 BOX_XYXYR = 0
 BOX_XYWLR = 1
+BOX_XYWLR_RRPN = 2
 
 
 class D3BError(RuntimeError):
@@ -112,6 +113,7 @@ SIGNATURES = {
     "d3b_predict_workspace_bytes": (_sz, [C.POINTER(PredictParams)]),
     "d3b_predict_task": (C.c_int, [C.POINTER(PredictParams), _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "d3b_boxes_iou_bev": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "d3b_rotate_iou_rrpn": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "d3b_nms_workspace_bytes": (_sz, [_i32]),
     "d3b_rotate_nms": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "d3b_normal_nms": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),

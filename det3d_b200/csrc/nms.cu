@@ -323,6 +323,134 @@ __device__ __forceinline__ bool suppresses_xywlr(const Quad& a, const Quad& b, f
   return ov >= thresh;
 }
 
+
+// ============================================================================
+// RRPN rotated IoU (numba rotate_iou_gpu / rotate_nms_gpu, det3d/ops/nms/nms_gpu.py:180-470).
+// Boxes are [cx, cy, w, l, r].  Types follow numba's typing of the reference source: float32
+// arithmetic throughout, except where an integer / float literal promotes to float64
+// (triangle areas "/ 2.0", the area accumulator, "center /= n", the final ratio).
+// ============================================================================
+__device__ __forceinline__ void rrpn_corners(const float* rb, float* c) {                  // :368-390
+  const float a_cos = cosf(rb[4]), a_sin = sinf(rb[4]);
+  const float hx = (float)((double)rb[2] / 2.0), hy = (float)((double)rb[3] / 2.0);
+  const float cx[4] = {-hx, -hx, hx, hx}, cy[4] = {-hy, hy, hy, -hy};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c[2 * i] = a_cos * cx[i] + a_sin * cy[i] + rb[0];
+    c[2 * i + 1] = -a_sin * cx[i] + a_cos * cy[i] + rb[1];
+  }
+}
+
+__device__ __forceinline__ bool rrpn_point_in_quad(float px, float py, const float* c) {    // :325-341
+  const float ab0 = c[2] - c[0], ab1 = c[3] - c[1];
+  const float ad0 = c[6] - c[0], ad1 = c[7] - c[1];
+  const float ap0 = px - c[0], ap1 = py - c[1];
+  const float abab = ab0 * ab0 + ab1 * ab1, abap = ab0 * ap0 + ab1 * ap1;
+  const float adad = ad0 * ad0 + ad1 * ad1, adap = ad0 * ap0 + ad1 * ap1;
+  return abab >= abap && abap >= 0.f && adad >= adap && adap >= 0.f;
+}
+
+__device__ __forceinline__ bool rrpn_segment_intersection(const float* p1, const float* p2, int i, int j,
+                                                          float* out) {                    // :239-281
+  const float A0 = p1[2 * i], A1 = p1[2 * i + 1];
+  const float B0 = p1[2 * ((i + 1) & 3)], B1 = p1[2 * ((i + 1) & 3) + 1];
+  const float C0 = p2[2 * j], C1 = p2[2 * j + 1];
+  const float D0 = p2[2 * ((j + 1) & 3)], D1 = p2[2 * ((j + 1) & 3) + 1];
+  const float BA0 = B0 - A0, BA1 = B1 - A1, DA0 = D0 - A0, CA0 = C0 - A0, DA1 = D1 - A1, CA1 = C1 - A1;
+  const bool acd = DA1 * CA0 > CA1 * DA0;
+  const bool bcd = (D1 - B1) * (C0 - B0) > (C1 - B1) * (D0 - B0);
+  if (acd != bcd) {
+    const bool abc = CA1 * BA0 > BA1 * CA0;
+    const bool abd = DA1 * BA0 > BA1 * DA0;
+    if (abc != abd) {
+      const float DC0 = D0 - C0, DC1 = D1 - C1;
+      const float ABBA = A0 * B1 - B0 * A1, CDDC = C0 * D1 - D0 * C1;
+      const float DH = BA1 * DC0 - BA0 * DC1;
+      const float Dx = ABBA * DC0 - BA0 * CDDC, Dy = ABBA * DC1 - BA1 * CDDC;
+      out[0] = Dx / DH;
+      out[1] = Dy / DH;
+      return true;
+    }
+  }
+  return false;
+}
+
+// intersection area of two rotated rectangles (`inter`, :393-408)
+__device__ double rrpn_inter(const float* rb1, const float* rb2) {
+  float c1[8], c2[8], pts[16];
+  rrpn_corners(rb1, c1);
+  rrpn_corners(rb2, c2);
+  int n = 0;                                                                                 // :344-365
+  // the reference writes into a 16-float buffer unchecked; two rectangles yield at most 8 points, the
+  // guard only matters for non-finite input
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (n < 8 && rrpn_point_in_quad(c1[2 * i], c1[2 * i + 1], c2)) { pts[2 * n] = c1[2 * i]; pts[2 * n + 1] = c1[2 * i + 1]; ++n; }
+    if (n < 8 && rrpn_point_in_quad(c2[2 * i], c2[2 * i + 1], c1)) { pts[2 * n] = c2[2 * i]; pts[2 * n + 1] = c2[2 * i + 1]; ++n; }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float t[2];
+      if (n < 8 && rrpn_segment_intersection(c1, c2, i, j, t)) { pts[2 * n] = t[0]; pts[2 * n + 1] = t[1]; ++n; }
+    }
+  if (n > 0) {                                                                               // :199-236
+    float cen0 = 0.f, cen1 = 0.f;
+    for (int i = 0; i < n; ++i) { cen0 += pts[2 * i]; cen1 += pts[2 * i + 1]; }
+    cen0 = (float)((double)cen0 / (double)n);
+    cen1 = (float)((double)cen1 / (double)n);
+    float vs[8];
+    for (int i = 0; i < n; ++i) {
+      float v0 = pts[2 * i] - cen0, v1 = pts[2 * i + 1] - cen1;
+      const float d = sqrtf(v0 * v0 + v1 * v1);
+      v0 = v0 / d;
+      v1 = v1 / d;
+      if (v1 < 0.f) v0 = (float)(-2.0 - (double)v0);
+      vs[i] = v0;
+    }
+    for (int i = 1; i < n; ++i) {
+      if (vs[i - 1] > vs[i]) {
+        const float temp = vs[i], tx = pts[2 * i], ty = pts[2 * i + 1];
+        int j = i;
+        while (j > 0 && vs[j - 1] > temp) {
+          vs[j] = vs[j - 1];
+          pts[2 * j] = pts[2 * j - 2];
+          pts[2 * j + 1] = pts[2 * j - 1];
+          --j;
+        }
+        vs[j] = temp;
+        pts[2 * j] = tx;
+        pts[2 * j + 1] = ty;
+      }
+    }
+  }
+  double area = 0.0;                                                                         // :185-196
+  for (int i = 0; i < n - 2; ++i) {
+    const float a0 = pts[0], a1 = pts[1], b0 = pts[2 * i + 2], b1 = pts[2 * i + 3], q0 = pts[2 * i + 4], q1 = pts[2 * i + 5];
+    area += fabs((double)((a0 - q0) * (b1 - q1) - (a1 - q1) * (b0 - q0)) / 2.0);
+  }
+  return area;
+}
+
+// devRotateIoUEval (:585-597): criterion -1 IoU, 0 inter/area1, 1 inter/area2, else the intersection area
+__device__ __forceinline__ double rrpn_iou(const float* rb1, const float* rb2, int criterion) {
+  const float area1 = rb1[2] * rb1[3], area2 = rb2[2] * rb2[3];
+  const double ai = rrpn_inter(rb1, rb2);
+  if (criterion == -1) return ai / ((double)(area1 + area2) - ai);
+  if (criterion == 0) return ai / (double)area1;
+  if (criterion == 1) return ai / (double)area2;
+  return ai;
+}
+
+// rotate_iou_kernel(_eval) (:499-538,600-640): out[n, k] = IoU(query[k], boxes[n])
+__global__ void __launch_bounds__(256)
+rrpn_matrix_kernel(int n, const float* __restrict__ boxes, int k, const float* __restrict__ query, int criterion,
+                   float* __restrict__ out) {
+  const int a = blockIdx.y * 16 + threadIdx.y;
+  const int b = blockIdx.x * 16 + threadIdx.x;
+  if (a >= n || b >= k) return;
+  out[(size_t)a * k + b] = (float)rrpn_iou(query + (size_t)b * 5, boxes + (size_t)a * 5, criterion);
+}
+
 // ============================================================================
 // kernels
 // ============================================================================
@@ -405,6 +533,8 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
           if (!(thresh >= 0.0f && surely_disjoint(dc, dcol[tx]))) bit = iou_xyxyr(cur_box, scol + tx * 5) > thresh;
         } else if (FMT == 1) {
           bit = suppresses_xywlr(qrow[rr], qcol[tx], thresh, nullptr);
+        } else if (FMT == 4) {
+          bit = rrpn_iou(cur_box, scol + tx * 5, -1) > (double)thresh;     // rotate_nms_kernel, nms_gpu.py:411-450
         } else if (FMT == 2) {
           bit = iou_axis_aligned(cur_box, scol + tx * 5) > thresh;
         } else {
@@ -510,6 +640,8 @@ static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* 
     nms_mask_kernel<1><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   else if (fmt_kernel == 2)
     nms_mask_kernel<2><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+  else if (fmt_kernel == 4)
+    nms_mask_kernel<4><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   else
     nms_mask_kernel<3><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
   D3B_LAUNCH_CHECK();
@@ -551,6 +683,18 @@ extern "C" int d3b_boxes_iou_bev(const float* boxes_a, int32_t na, const float* 
   return D3B_OK;
 }
 
+extern "C" int d3b_rotate_iou_rrpn(const float* boxes, int32_t n, const float* query_boxes, int32_t k,
+                                   int32_t criterion, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(n >= 0 && k >= 0, "d3b_rotate_iou_rrpn: bad argument");
+  if (n == 0 || k == 0) return D3B_OK;
+  D3B_REQUIRE(boxes && query_boxes && out, "d3b_rotate_iou_rrpn: null argument");
+  dim3 blocks(div_up(k, 16), div_up(n, 16)), threads(16, 16);
+  rrpn_matrix_kernel<<<blocks, threads, 0, stream>>>(n, boxes, k, query_boxes, criterion, out);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
 extern "C" size_t d3b_nms_workspace_bytes(int32_t n_cap) {
   if (n_cap <= 0) return 16;
   return align_up((size_t)n_cap * div_up(n_cap, kNmsBlock) * 8);
@@ -561,13 +705,14 @@ extern "C" int d3b_rotate_nms(const float* boxes, int32_t n_cap, const int32_t* 
                               void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   D3B_REQUIRE(n_cap >= 0 && max_keep >= 0 && keep_count, "d3b_rotate_nms: bad argument");
-  D3B_REQUIRE(fmt == D3B_BOX_XYXYR || fmt == D3B_BOX_XYWLR, "d3b_rotate_nms: unknown box format %d", fmt);
+  D3B_REQUIRE(fmt == D3B_BOX_XYXYR || fmt == D3B_BOX_XYWLR || fmt == D3B_BOX_XYWLR_RRPN,
+              "d3b_rotate_nms: unknown box format %d", fmt);
   if (n_cap == 0 || max_keep == 0) {
     D3B_CUDA(cudaMemsetAsync(keep_count, 0, 4, stream));
     return D3B_OK;
   }
   D3B_REQUIRE(boxes && keep_idx && workspace, "d3b_rotate_nms: null argument");
-  return nms_common(fmt == D3B_BOX_XYXYR ? 0 : 1, boxes, n_cap, n_boxes_dev, thresh, max_keep,
+  return nms_common(fmt == D3B_BOX_XYXYR ? 0 : (fmt == D3B_BOX_XYWLR ? 1 : 4), boxes, n_cap, n_boxes_dev, thresh, max_keep,
                     (long long*)keep_idx, keep_count, workspace, workspace_bytes, stream);
 }
 

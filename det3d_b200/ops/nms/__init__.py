@@ -1,1 +1,2 @@
 from . import nms_ops
+from .nms_gpu import nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval, rotate_nms_gpu

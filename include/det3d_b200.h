@@ -218,11 +218,18 @@ int d3b_rulebook_dense2d(int32_t batch, int32_t height, int32_t width, const int
  * ========================================================================= */
 #define D3B_BOX_XYXYR 0   /* [x1,y1,x2,y2,ry]: det3d/ops/iou3d/src/iou3d_kernel.cu:108-221 */
 #define D3B_BOX_XYWLR 1   /* [cx,cy,w,l,r]  : det3d/ops/nms/nms_cpu.py:34-45 + nms_cpu.h:73-169 */
+#define D3B_BOX_XYWLR_RRPN 2 /* [cx,cy,w,l,r]: numba RRPN routine, det3d/ops/nms/nms_gpu.py:180-470 */
 
 /* Pairwise rotated IoU (mode 0) or overlap area (mode 1), out [na, nb].
  * replaces boxes_iou_bev_gpu / boxes_overlap_bev_gpu, det3d/ops/iou3d/src/iou3d.cpp:31-71 */
 int d3b_boxes_iou_bev(const float* boxes_a, int32_t na, const float* boxes_b, int32_t nb,
                       int32_t mode, float* out, void* stream);
+
+/* RRPN rotated IoU matrix, out[n, k] = f(query[k], boxes[n]); criterion -1: IoU, 0: inter / area(query),
+ * 1: inter / area(box), other: intersection area.  replaces rotate_iou_gpu / rotate_iou_gpu_eval,
+ * det3d/ops/nms/nms_gpu.py:499-669 (numba.cuda). */
+int d3b_rotate_iou_rrpn(const float* boxes, int32_t n, const float* query_boxes, int32_t k,
+                        int32_t criterion, float* out, void* stream);
 
 size_t d3b_nms_workspace_bytes(int32_t n_cap);
 
@@ -230,6 +237,7 @@ size_t d3b_nms_workspace_bytes(int32_t n_cap);
  * fmt = D3B_BOX_XYXYR: suppress when iou >  thresh   (iou3d.cpp:73-120, nms_gpu)
  * fmt = D3B_BOX_XYWLR: suppress when iou >= thresh and the axis-aligned hulls
  *                      overlap                         (nms_cpu.h:73-169)
+ * fmt = D3B_BOX_XYWLR_RRPN: suppress when iou > thresh (rotate_nms_gpu, nms_gpu.py:411-496)
  * n_boxes may be a device count (n_boxes_dev != NULL, bounded by n_cap).
  * keep_idx [min(n_cap, max_keep)] i64 device receives kept positions in
  * ascending order, keep_count [1] i32 device their number (<= max_keep). */

@@ -250,3 +250,130 @@ int64_t oracle_rotate_nms_cc(const float* dets, const int32_t* order, int64_t n,
   free(sup); free(q);
   return nk;
 }
+
+/* ==========================================================================
+ * (C) RRPN rotated IoU -- restatement of the numba.cuda device functions
+ *     det3d/ops/nms/nms_gpu.py:180-470 (rotate_iou_gpu / rotate_nms_gpu).
+ *     Boxes [cx,cy,w,l,r].  float where numba types float32, double where a
+ *     literal promotes (":185-196" areas, "center /= n", the final ratio).
+ *     Pinned by tests/golden/rrpn_600.npz (reference source compiled for CPU).
+ * ========================================================================== */
+static void rrpn_corners(const float* rb, float* c) {                                  /* :368-390 */
+  float a_cos = cosf(rb[4]), a_sin = sinf(rb[4]);
+  float hx = (float)((double)rb[2] / 2.0), hy = (float)((double)rb[3] / 2.0);
+  float cx[4] = {-hx, -hx, hx, hx}, cy[4] = {-hy, hy, hy, -hy};
+  for (int i = 0; i < 4; ++i) {
+    c[2 * i] = a_cos * cx[i] + a_sin * cy[i] + rb[0];
+    c[2 * i + 1] = -a_sin * cx[i] + a_cos * cy[i] + rb[1];
+  }
+}
+static int rrpn_point_in_quad(float px, float py, const float* c) {                    /* :325-341 */
+  float ab0 = c[2] - c[0], ab1 = c[3] - c[1], ad0 = c[6] - c[0], ad1 = c[7] - c[1];
+  float ap0 = px - c[0], ap1 = py - c[1];
+  float abab = ab0 * ab0 + ab1 * ab1, abap = ab0 * ap0 + ab1 * ap1;
+  float adad = ad0 * ad0 + ad1 * ad1, adap = ad0 * ap0 + ad1 * ap1;
+  return abab >= abap && abap >= 0 && adad >= adap && adap >= 0;
+}
+static int rrpn_seg(const float* p1, const float* p2, int i, int j, float* out) {      /* :239-281 */
+  float A0 = p1[2 * i], A1 = p1[2 * i + 1], B0 = p1[2 * ((i + 1) % 4)], B1 = p1[2 * ((i + 1) % 4) + 1];
+  float C0 = p2[2 * j], C1 = p2[2 * j + 1], D0 = p2[2 * ((j + 1) % 4)], D1 = p2[2 * ((j + 1) % 4) + 1];
+  float BA0 = B0 - A0, BA1 = B1 - A1, DA0 = D0 - A0, CA0 = C0 - A0, DA1 = D1 - A1, CA1 = C1 - A1;
+  int acd = DA1 * CA0 > CA1 * DA0;
+  int bcd = (D1 - B1) * (C0 - B0) > (C1 - B1) * (D0 - B0);
+  if (acd != bcd) {
+    int abc = CA1 * BA0 > BA1 * CA0, abd = DA1 * BA0 > BA1 * DA0;
+    if (abc != abd) {
+      float DC0 = D0 - C0, DC1 = D1 - C1, ABBA = A0 * B1 - B0 * A1, CDDC = C0 * D1 - D0 * C1;
+      float DH = BA1 * DC0 - BA0 * DC1, Dx = ABBA * DC0 - BA0 * CDDC, Dy = ABBA * DC1 - BA1 * CDDC;
+      out[0] = Dx / DH;
+      out[1] = Dy / DH;
+      return 1;
+    }
+  }
+  return 0;
+}
+static double rrpn_inter(const float* rb1, const float* rb2) {                         /* :393-408 */
+  float c1[8], c2[8], pts[16], t[2];
+  rrpn_corners(rb1, c1);
+  rrpn_corners(rb2, c2);
+  int n = 0;
+  for (int i = 0; i < 4; ++i) {                                                         /* :344-365 */
+    if (n < 8 && rrpn_point_in_quad(c1[2 * i], c1[2 * i + 1], c2)) { pts[2 * n] = c1[2 * i]; pts[2 * n + 1] = c1[2 * i + 1]; ++n; }
+    if (n < 8 && rrpn_point_in_quad(c2[2 * i], c2[2 * i + 1], c1)) { pts[2 * n] = c2[2 * i]; pts[2 * n + 1] = c2[2 * i + 1]; ++n; }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (n < 8 && rrpn_seg(c1, c2, i, j, t)) { pts[2 * n] = t[0]; pts[2 * n + 1] = t[1]; ++n; }
+  if (n > 0) {                                                                          /* :199-236 */
+    float cen0 = 0.f, cen1 = 0.f, vs[8];
+    for (int i = 0; i < n; ++i) { cen0 += pts[2 * i]; cen1 += pts[2 * i + 1]; }
+    cen0 = (float)((double)cen0 / (double)n);
+    cen1 = (float)((double)cen1 / (double)n);
+    for (int i = 0; i < n; ++i) {
+      float v0 = pts[2 * i] - cen0, v1 = pts[2 * i + 1] - cen1;
+      float d = sqrtf(v0 * v0 + v1 * v1);
+      v0 = v0 / d;
+      v1 = v1 / d;
+      if (v1 < 0) v0 = (float)(-2.0 - (double)v0);
+      vs[i] = v0;
+    }
+    for (int i = 1; i < n; ++i) {
+      if (vs[i - 1] > vs[i]) {
+        float temp = vs[i], tx = pts[2 * i], ty = pts[2 * i + 1];
+        int j = i;
+        while (j > 0 && vs[j - 1] > temp) {
+          vs[j] = vs[j - 1];
+          pts[2 * j] = pts[2 * j - 2];
+          pts[2 * j + 1] = pts[2 * j - 1];
+          --j;
+        }
+        vs[j] = temp;
+        pts[2 * j] = tx;
+        pts[2 * j + 1] = ty;
+      }
+    }
+  }
+  double area = 0.0;                                                                    /* :185-196 */
+  for (int i = 0; i < n - 2; ++i)
+    area += fabs((double)((pts[0] - pts[2 * i + 4]) * (pts[2 * i + 3] - pts[2 * i + 5]) -
+                          (pts[1] - pts[2 * i + 5]) * (pts[2 * i + 2] - pts[2 * i + 4])) / 2.0);
+  return area;
+}
+
+/* devRotateIoUEval :585-597 */
+double oracle_rrpn_iou(const float* rb1, const float* rb2, int criterion) {
+  float area1 = rb1[2] * rb1[3], area2 = rb2[2] * rb2[3];
+  double ai = rrpn_inter(rb1, rb2);
+  if (criterion == -1) return ai / ((double)(area1 + area2) - ai);
+  if (criterion == 0) return ai / (double)area1;
+  if (criterion == 1) return ai / (double)area2;
+  return ai;
+}
+
+/* rotate_iou_kernel_eval :600-640: out[n,k] = f(query[k], boxes[n]) */
+void oracle_rrpn_iou_matrix(const float* boxes, int n, const float* query, int k, int criterion, float* out) {
+#pragma omp parallel for
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < k; ++b) out[(size_t)a * k + b] = (float)oracle_rrpn_iou(query + 5 * b, boxes + 5 * a, criterion);
+}
+
+/* rotate_nms_gpu :453-496 (mask kernel :411-450 + nms_postprocess :110-127).  dets [n,6] = cx,cy,w,l,r,score,
+ * `order` = argsort(score)[::-1]; keep[] receives ORIGINAL indices.  near[0] counts tested pairs whose IoU lies
+ * within 1e-5 of the threshold (their outcome may differ between sin/cos implementations). */
+int64_t oracle_rrpn_nms(const float* dets, const int32_t* order, int64_t n, float thresh, int64_t* keep, int64_t* near) {
+  uint8_t* sup = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
+  int64_t nk = 0, nn = 0;
+  for (int64_t _i = 0; _i < n; ++_i) {
+    if (sup[_i]) continue;
+    int64_t i = order[_i];
+    keep[nk++] = i;
+    for (int64_t _j = _i + 1; _j < n; ++_j) {
+      double iou = oracle_rrpn_iou(dets + 6 * i, dets + 6 * order[_j], -1);
+      if (fabs(iou - (double)thresh) < 1e-5) ++nn;
+      if (iou > (double)thresh) sup[_j] = 1;
+    }
+  }
+  if (near) near[0] = nn;
+  free(sup);
+  return nk;
+}

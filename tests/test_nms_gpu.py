@@ -176,3 +176,32 @@ def test_box_torch_ops_nms_pixel_matches_reference_golden(thr):
     want = top[nms_pixel(g["dets"][top], thr)][:50]
     assert np.array_equal(k2.cpu().numpy(), want)
     assert box_torch_ops.nms(dets[:0, :4], dets[:0, 4]).shape == (0,)
+
+
+def test_rrpn_rotate_iou_and_nms_match_reference_golden():
+    """a13: det3d.ops.nms.{rotate_iou_gpu, rotate_iou_gpu_eval, rotate_nms_gpu, nms_gpu} (numpy in/out)."""
+    from conftest import load_golden
+    from det3d.ops.nms import nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval, rotate_nms_gpu
+    from oracle import rrpn
+    g = load_golden("rrpn_600")
+    a = g["mat_boxes"]
+    for crit in (-1, 0, 1, 2):
+        got = rotate_iou_gpu_eval(a, a[:37], crit)
+        want = g["mat_c%d" % (crit + 1)][:, :37]
+        assert got.shape == want.shape and got.dtype == np.float32
+        both = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), both)
+        assert float(np.abs(got[both] - want[both]).max()) <= 1e-5
+    assert np.array_equal(rotate_iou_gpu(a, a[:5]), rotate_iou_gpu_eval(a, a[:5], -1))
+    assert rotate_iou_gpu(a[:0], a).shape == (0, a.shape[0])
+    for thr in (0.1, 0.3, 0.5):
+        keep = np.asarray(rotate_nms_gpu(g["dets"], thr), np.int64)
+        want = g["keep_t%02d" % int(thr * 100)]
+        _, near = rrpn.rotate_nms(g["dets"], thr)
+        if near == 0:
+            assert np.array_equal(keep, want)
+        else:
+            assert len(set(keep.tolist()) ^ set(want.tolist())) <= 2 * near
+    ga = load_golden("aa_nms_pixel_700")
+    assert np.array_equal(np.asarray(nms_gpu(ga["dets"], 0.5), np.int64), ga["keep_t50"])
+    assert rotate_nms_gpu(np.zeros((0, 6), np.float32), 0.5) == []

@@ -94,3 +94,28 @@ def test_axis_aligned_pixel_nms_oracle_matches_reference_golden():
     assert np.array_equal(iou[g["pair_idx"][:, 0], g["pair_idx"][:, 1]], g["pair_iou"])      # bit-exact float64
     for thr in (0.3, 0.5, 0.7):
         assert np.array_equal(nms_pixel(g["dets"], thr), g["keep_t%02d" % int(thr * 100)])
+
+
+def test_rrpn_oracle_matches_reference_golden():
+    """a13: the numba RRPN rotated IoU / NMS; golden = the reference source compiled for the CPU target."""
+    import math
+    from conftest import load_golden
+    from oracle import rrpn
+    g = load_golden("rrpn_600")
+    a = g["mat_boxes"]
+    for crit in (-1, 0, 1, 2):
+        got = rrpn.rotate_iou_eval(a, a, crit)
+        want = g["mat_c%d" % (crit + 1)]
+        both = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), both)
+        assert float(np.abs(got[both] - want[both]).max()) <= 1e-5
+    iou = rrpn.rotate_iou_eval(a, a, -1)
+    assert abs(iou[0, 1] - 1 / math.sqrt(2)) < 1e-6          # unit square vs itself rotated 45 deg (SURVEY 8c KAT)
+    assert abs(iou[0, 2] - 1.0) < 1e-6 and iou[0, 3] == 0.0    # identical, disjoint
+    for thr in (0.1, 0.3, 0.5):
+        keep, near = rrpn.rotate_nms(g["dets"], thr)
+        want = g["keep_t%02d" % int(thr * 100)]
+        if near == 0:
+            assert np.array_equal(keep, want)
+        else:
+            assert len(set(keep.tolist()) ^ set(want.tolist())) <= 2 * near
