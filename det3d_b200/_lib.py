@@ -68,6 +68,7 @@ class ConvParams(C.Structure):
         ("in_scale", C.c_void_p),
         ("in_shift", C.c_void_p),
         ("in_relu", C.c_int32),
+        ("out_zeroed", C.c_int32),
     ]
 
 
@@ -105,6 +106,7 @@ SIGNATURES = {
     "d3b_conv_pack_weight": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "d3b_sparse_conv": (C.c_int, [_vp, _vp, _vp, _vp, _i32, C.POINTER(ConvParams), _vp, _vp]),
     "d3b_rulebook_pairs": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "d3b_zero_rows": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "d3b_feature_epilogue": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "d3b_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_pillar_features": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),

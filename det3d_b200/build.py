@@ -91,7 +91,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("det3d_b200: CUDA build failed")
     # libcuda is NOT linked: CPU-only hosts must be able to dlopen the library
     # (driver entry points, if needed, are resolved with cudaGetDriverEntryPoint).
-    link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs
+    link = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH] + objs
     subprocess.run(link, check=True)
     with open(STAMP, "w") as fh:
         fh.write(_digest())

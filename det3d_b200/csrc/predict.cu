@@ -5,16 +5,19 @@
 //   sigmoid scores -> score filter -> top-`nms_pre_max_size` -> anchor decode
 //   (det3d/core/bbox/box_torch_ops.py:80-148) -> rotated NMS (-> csrc/nms.cu) ->
 //   direction fix -> post_center_limit_range mask,
-// as five launches over fixed-size buffers:
+// as six launches over fixed-size buffers:
 //   P1 head_scores     best logit / label per anchor straight from the (possibly strided) head rows
-//   P2 topk_select     one CTA per sample: 4-pass radix select of the k-th largest logit, ordered
-//                      gather of the winners, bitonic sort (value desc, index asc)
+//   P2 topk            histogram of the leading key bits (built inside P1) -> partition kernel appends the pivot
+//                      bin and everything above it to a candidate list -> one CTA per sample sorts the list
+//                      (value desc, index asc) in shared memory and emits the first k
 //   P3 decode_selected decode ONLY the k selected anchors (the reference decodes all 70,400),
 //                      sigmoid, direction label, count of scores >= threshold (a prefix, scores are sorted)
 //   -- d3b_rotate_nms / d3b_normal_nms on the k candidates (n_valid read on the device) --
 //   P4 finalize        gather the kept boxes, direction flip, range mask -> packed [B, post, nd+3] rows
 // Selection is identical to the reference's "filter, then top-k": sigmoid is monotonic, so the
 // passing set is a prefix of the top-k by logit.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace d3b {
@@ -28,14 +31,21 @@ __device__ __forceinline__ unsigned int float_to_ordered(float f) {
 }
 
 // ---- P1 -------------------------------------------------------------------------------------
+// grid = (CTAs per sample, batch).  Besides the best logit / label per anchor, every CTA builds a histogram of
+// the top kTopkBinBits bits of the order-preserving key in shared memory and adds its non-empty bins to the
+// sample's global histogram: the first radix-select pass of P2 at full-GPU width.
+constexpr int kTopkBinBits = 11;
+constexpr int kTopkBins = 1 << kTopkBinBits;
+
 __global__ void __launch_bounds__(256)
-head_scores_kernel(const float* __restrict__ cls, int row_stride, int col0, int batch, int hw, int na,
-                   int n_cls, float* __restrict__ best_logit, unsigned char* __restrict__ best_label) {
-  const int A = hw * na;
-  const long long total = (long long)batch * A;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(e / A), i = (int)(e - (long long)b * A);
+head_scores_kernel(const float* __restrict__ cls, int row_stride, int col0, int hw, int na, int n_cls,
+                   float* __restrict__ best_logit, unsigned char* __restrict__ best_label,
+                   unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_hist[kTopkBins];
+  const int A = hw * na, b = blockIdx.y;
+  for (int j = threadIdx.x; j < kTopkBins; j += blockDim.x) s_hist[j] = 0u;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
     const int cell = i / na, a = i - cell * na;
     const float* p = cls + ((size_t)b * hw + cell) * row_stride + col0 + a * n_cls;
     float best = p[0];
@@ -44,97 +54,141 @@ head_scores_kernel(const float* __restrict__ cls, int row_stride, int col0, int 
       const float v = p[c];
       if (v > best) { best = v; lab = c; }    // first maximum wins, like torch.max
     }
-    best_logit[e] = best;
-    best_label[e] = (unsigned char)lab;
+    best_logit[(size_t)b * A + i] = best;
+    best_label[(size_t)b * A + i] = (unsigned char)lab;
+    atomicAdd(&s_hist[float_to_ordered(best) >> (32 - kTopkBinBits)], 1u);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < kTopkBins; j += blockDim.x) {
+    const unsigned int c = s_hist[j];
+    if (c != 0u) atomicAdd(&hist[(size_t)b * kTopkBins + j], c);
   }
 }
 
 // ---- P2 -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTopkThreads)
-topk_select_kernel(const float* __restrict__ values, int A, int k, float* __restrict__ out_val,
-                   int* __restrict__ out_idx) {
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int s_prefix, s_remaining;
-  __shared__ unsigned int sel_key[kTopkMax];
-  __shared__ int sel_idx[kTopkMax];
-  __shared__ int s_count, s_ties_taken;
-  __shared__ int warp_tot[32];
-  const float* v = values + (size_t)blockIdx.x * A;
-  float* ov = out_val + (size_t)blockIdx.x * k;
-  int* oi = out_idx + (size_t)blockIdx.x * k;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Selection order everywhere: (logit descending, anchor index ascending) -- expressed as one unique 64-bit
+// composite  key << 32 | (0xffffffff - index)  sorted descending, so ties need no special handling.
+__device__ __forceinline__ unsigned long long topk_composite(float v, int index) {
+  return ((unsigned long long)float_to_ordered(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)index);
+}
 
-  // radix select: find the key of the k-th largest element
-  if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned int)k; }
+// P2a, grid = (CTAs per sample, batch): find the pivot bin (the highest bin p with count(bin >= p) >= k) from the
+// sample's histogram and append every anchor in a bin >= p to the sample's candidate list (warp-aggregated).
+// The list holds the k winners plus the rest of the pivot bin -- typically k + a few hundred entries.
+__global__ void __launch_bounds__(256)
+topk_partition_kernel(const float* __restrict__ values, const unsigned int* __restrict__ hist, int A, int k,
+                      unsigned long long* __restrict__ part, int* __restrict__ part_count) {
+  __shared__ unsigned int s_group[256];
+  __shared__ int s_g, s_pivot;
+  __shared__ unsigned int s_acc;
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  constexpr int kPer = kTopkBins / 256;
+  unsigned int local[kPer], sum = 0u;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) { local[j] = hist[(size_t)b * kTopkBins + tid * kPer + j]; sum += local[j]; }
+  s_group[tid] = sum;
+  if (tid == 0) { s_g = 0; s_acc = 0u; s_pivot = 0; }
   __syncthreads();
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    for (int j = tid; j < 256; j += kTopkThreads) hist[j] = 0u;
+  if (tid == 0) {
+    unsigned int acc = 0u;
+    for (int g = 255; g >= 0; --g) {
+      if (acc + s_group[g] >= (unsigned int)k) { s_g = g; s_acc = acc; break; }
+      acc += s_group[g];
+    }
+  }
+  __syncthreads();
+  if (tid == s_g) {
+    unsigned int acc = s_acc;
+    int pivot = tid * kPer;
+#pragma unroll
+    for (int j = kPer - 1; j >= 0; --j) {
+      acc += local[j];
+      if (acc >= (unsigned int)k) { pivot = tid * kPer + j; break; }
+    }
+    s_pivot = pivot;
+  }
+  __syncthreads();
+  const unsigned int pivot = (unsigned int)s_pivot;
+  const float* v = values + (size_t)b * A;
+  unsigned long long* out = part + (size_t)b * A;
+  const int a_pad = (A + 31) / 32 * 32;
+  for (int i = blockIdx.x * blockDim.x + tid; i < a_pad; i += gridDim.x * blockDim.x) {
+    const float x = i < A ? v[i] : 0.f;
+    const bool take = i < A && (float_to_ordered(x) >> (32 - kTopkBinBits)) >= pivot;
+    const unsigned int bal = __ballot_sync(0xffffffffu, take);
+    if (bal == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&part_count[b], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) out[base + __popc(bal & ((1u << lane) - 1u))] = topk_composite(x, i);
+  }
+}
+
+// P2b, one CTA per sample: sort the candidate list in shared memory and emit the first k.  A list longer than
+// kTopkSortCap (a huge pivot bin, e.g. constant logits) is first cut down to exactly k entries by a radix select
+// over the composites (unique, so the k-th largest is a strict threshold).
+constexpr int kTopkSortCap = 8192;
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_finish_kernel(const unsigned long long* __restrict__ part, const int* __restrict__ part_count, int A, int k,
+                   float* __restrict__ out_val, int* __restrict__ out_idx) {
+  extern __shared__ unsigned long long buf[];                  // [kTopkSortCap]
+  __shared__ unsigned int hist[kTopkBins];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_remaining;
+  __shared__ int s_count;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const unsigned long long* list = part + (size_t)b * A;
+  const int n = min(part_count[b], A);
+  int m = n;
+  if (n <= kTopkSortCap) {
+    for (int j = tid; j < n; j += kTopkThreads) buf[j] = list[j];
+  } else {
+    if (tid == 0) { s_prefix = 0ull; s_remaining = (unsigned int)k; }
     __syncthreads();
-    const unsigned int prefix = s_prefix;
-    const unsigned int pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    // warp-aggregated histogram: detector logits share their leading bits, so per-element shared-memory
-    // atomics would all land on one or two bins and serialise
-    const int a_pad = (A + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
-    for (int i = tid; i < a_pad; i += kTopkThreads) {
-      int digit = -1;   // lanes outside the prefix share one tag (a single match group, no atomic)
-      if (i < A) {
-        const unsigned int key = float_to_ordered(v[i]);
-        if ((key & pmask) == prefix) digit = (int)((key >> shift) & 255u);
+    int consumed = 0;
+    while (consumed < 64) {
+      const int bits = min(kTopkBinBits, 64 - consumed);
+      const int shift = 64 - consumed - bits;
+      for (int j = tid; j < kTopkBins; j += kTopkThreads) hist[j] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int j = tid; j < n; j += kTopkThreads) {
+        const unsigned long long c = list[j];
+        if (consumed == 0 || (c >> (64 - consumed)) == (prefix >> (64 - consumed)))
+          atomicAdd(&hist[(unsigned int)(c >> shift) & ((1u << bits) - 1u)], 1u);
       }
-      const unsigned int peers = __match_any_sync(0xffffffffu, digit);
-      if (digit >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int rem = s_remaining, d = 255;
-      for (;; --d) {                       // walk digits from the top
-        const unsigned int c = hist[d];
-        if (c >= rem || d == 0) break;
-        rem -= c;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int rem = s_remaining;
+        int d = (1 << bits) - 1;
+        for (;; --d) {
+          const unsigned int c = hist[d];
+          if (c >= rem || d == 0) break;
+          rem -= c;
+        }
+        s_prefix = prefix | ((unsigned long long)d << shift);
+        s_remaining = rem;
       }
-      s_prefix = prefix | (d << shift);
-      s_remaining = rem;                   // how many elements equal to the pivot digit-prefix are still needed
+      __syncthreads();
+      consumed += bits;
+    }
+    const unsigned long long pivot = s_prefix;               // the k-th largest composite
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int j = tid; j < n; j += kTopkThreads) {
+      const unsigned long long c = list[j];
+      if (c >= pivot) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < kTopkSortCap) buf[pos] = c;
+      }
     }
     __syncthreads();
+    m = min(s_count, kTopkSortCap);
   }
-  const unsigned int pivot = s_prefix;     // key of the k-th largest
-  const int ties_needed = (int)s_remaining;
-  if (tid == 0) { s_count = 0; s_ties_taken = 0; }
-  __syncthreads();
-  // winners strictly above the pivot: order is fixed by the sort below
-  for (int i = tid; i < A; i += kTopkThreads) {
-    const unsigned int key = float_to_ordered(v[i]);
-    if (key > pivot) {
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < kTopkMax) { sel_key[pos] = key; sel_idx[pos] = i; }
-    }
-  }
-  __syncthreads();
-  const int n_gt = s_count;
-  // ties: the lowest indices win (deterministic): ordered pass in chunks of kTopkThreads
-  for (int base = 0; base < A && s_ties_taken < ties_needed; base += kTopkThreads) {
-    const int i = base + tid;
-    const bool tie = i < A && float_to_ordered(v[i]) == pivot;
-    const unsigned int bal = __ballot_sync(0xffffffffu, tie);
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int before = s_ties_taken;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-    const int rank = before + __popc(bal & ((1u << lane) - 1u));
-    if (tie && rank < ties_needed) { sel_key[n_gt + rank] = pivot; sel_idx[n_gt + rank] = i; }
-    __syncthreads();
-    if (tid == 0) {
-      int t = s_ties_taken;
-      for (int w = 0; w < kTopkThreads / 32; ++w) t += warp_tot[w];
-      s_ties_taken = t;
-    }
-    __syncthreads();
-  }
-  // pad to a power of two and bitonic-sort descending by (key, -index)
-  int n2 = 1;
-  while (n2 < k) n2 <<= 1;
-  for (int j = k + tid; j < n2; j += kTopkThreads) { sel_key[j] = 0u; sel_idx[j] = 0x7fffffff; }
+  int n2 = 2;
+  while (n2 < m) n2 <<= 1;
+  for (int j = m + tid; j < n2; j += kTopkThreads) buf[j] = 0ull;
   __syncthreads();
   for (int size = 2; size <= n2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -142,19 +196,20 @@ topk_select_kernel(const float* __restrict__ values, int A, int k, float* __rest
         const int lo = 2 * t - (t & (stride - 1));
         const int hi = lo + stride;
         const bool desc = (lo & size) == 0;
-        const unsigned int ka = sel_key[lo], kb = sel_key[hi];
-        const int ia = sel_idx[lo], ib = sel_idx[hi];
-        const bool a_first = ka > kb || (ka == kb && ia < ib);   // a should precede b in descending order
-        if (a_first != desc) { sel_key[lo] = kb; sel_key[hi] = ka; sel_idx[lo] = ib; sel_idx[hi] = ia; }
+        const unsigned long long ca = buf[lo], cb = buf[hi];
+        if ((ca > cb) != desc) { buf[lo] = cb; buf[hi] = ca; }
       }
       __syncthreads();
     }
   }
+  float* ov = out_val + (size_t)b * k;
+  int* oi = out_idx + (size_t)b * k;
   for (int j = tid; j < k; j += kTopkThreads) {
-    const unsigned int key = sel_key[j];
+    const unsigned long long c = buf[j];
+    const unsigned int key = (unsigned int)(c >> 32);
     const unsigned int u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
     ov[j] = __uint_as_float(u);
-    oi[j] = sel_idx[j];
+    oi[j] = (int)(0xffffffffu - (unsigned int)c);
   }
 }
 
@@ -269,7 +324,8 @@ finalize_kernel(PredictDev p, const float* __restrict__ cand, const float* __res
 }
 
 struct PredictWs {
-  float* best_logit; unsigned char* best_label; float* sel_logit; int* sel_idx; float* cand; float* nms_boxes;
+  float* best_logit; unsigned char* best_label; unsigned int* hist; int* part_count; unsigned long long* part;
+  float* sel_logit; int* sel_idx; float* cand; float* nms_boxes;
   float* scores; int* labels; int* dir_labels; int* n_valid; long long* keep_idx; int* keep_count; char* nms_ws;
   size_t nms_ws_bytes, bytes;
 };
@@ -281,6 +337,9 @@ static PredictWs carve_predict(const d3b_predict_params* q, char* base) {
   const size_t A = (size_t)q->hw * q->na, B = q->batch, k = q->pre_max, post = q->post_max;
   w.best_logit = (float*)take(B * A * 4);
   w.best_label = (unsigned char*)take(B * A);
+  w.hist = (unsigned int*)take(B * kTopkBins * 4 + B * 4);     // histogram + list counters: one memset
+  w.part_count = (int*)(w.hist ? w.hist + B * kTopkBins : nullptr);
+  w.part = (unsigned long long*)take(B * A * 8);
   w.sel_logit = (float*)take(B * k * 4);
   w.sel_idx = (int*)take(B * k * 4);
   w.cand = (float*)take(B * k * q->nd * 4);
@@ -342,10 +401,20 @@ extern "C" int d3b_predict_task(const d3b_predict_params* q, float* packed, int3
   for (int c = 0; c < 6; ++c) p.range[c] = q->post_center_range[c];
   p.has_range = q->has_range; p.label_offset = q->label_offset;
 
-  head_scores_kernel<<<grid_for((long long)q->batch * A, 256), 256, 0, stream>>>(
-      q->cls, q->cls_row_stride, q->cls_col0, q->batch, q->hw, q->na, q->n_cls, w.best_logit, w.best_label);
+  static bool finish_attr = false;
+  if (!finish_attr) {
+    D3B_CUDA(cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopkSortCap * 8));
+    finish_attr = true;
+  }
+  D3B_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)q->batch * (kTopkBins + 1) * 4, stream));
+  const dim3 sample_grid((unsigned)std::min(div_up(A, 512), kNumSMs), (unsigned)q->batch);
+  head_scores_kernel<<<sample_grid, 256, 0, stream>>>(q->cls, q->cls_row_stride, q->cls_col0, q->hw, q->na, q->n_cls,
+                                                      w.best_logit, w.best_label, w.hist);
   D3B_LAUNCH_CHECK();
-  topk_select_kernel<<<q->batch, kTopkThreads, 0, stream>>>(w.best_logit, A, q->pre_max, w.sel_logit, w.sel_idx);
+  topk_partition_kernel<<<sample_grid, 256, 0, stream>>>(w.best_logit, w.hist, A, q->pre_max, w.part, w.part_count);
+  D3B_LAUNCH_CHECK();
+  topk_finish_kernel<<<q->batch, kTopkThreads, kTopkSortCap * 8, stream>>>(w.part, w.part_count, A, q->pre_max,
+                                                                          w.sel_logit, w.sel_idx);
   D3B_LAUNCH_CHECK();
   D3B_CUDA(cudaMemsetAsync(w.n_valid, 0, (size_t)q->batch * 4, stream));
   decode_selected_kernel<<<grid_for((long long)q->batch * q->pre_max, 256), 256, 0, stream>>>(

@@ -441,7 +441,21 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
     const bool has_act = in_scale != nullptr || in_bias != nullptr || in_relu;
     uint32_t seq = 0;                     // CTA-local item ordinal
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++seq) {
-      if ((int)(seq % kPairGroups) != group) continue;
+      // Which 32-channel slices of this item the group fills.  A group waits for a stage on the parity of its
+      // empty barrier, which is only unambiguous if the previous use of that stage is known to have been consumed;
+      // a group's own earlier slots provide that guarantee when they are at most kStages - 1 slots behind, so the
+      // split keeps every group's consecutive slots close: items alternate between the groups for n_kb <= 2,
+      // both groups take half of every item for n_kb == 4, and the (unused by the named configs) n_kb == 3 case
+      // runs on one group.
+      int kb_begin = 0, kb_end = n_kb;
+      if (n_kb == 4) {
+        kb_begin = 2 * group;
+        kb_end = kb_begin + 2;
+      } else if (n_kb == 3) {
+        if (group != 0) continue;
+      } else if ((int)(seq % kPairGroups) != group) {
+        continue;
+      }
       const int k = item_k(item);
       const int first = (item - chunk_prefix[k]) * kTcTileM;
       const int cnt = count_s[k];
@@ -452,7 +466,7 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
         const int row = wq * 32 + 4 * q + g;
         src[q] = first + row < cnt ? __ldg(pin + row) : -1;
       }
-      for (int kb0 = 0; kb0 < n_kb; kb0 += 2) {
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += 2) {
         float4 v[2][8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -460,13 +474,14 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             v[h][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src[q] >= 0 && ch < c_in) v[h][q] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src[q] * c_in + ch));
+            if (src[q] >= 0 && ch < c_in && kb0 + h < kb_end)
+              v[h][q] = __ldg(reinterpret_cast<const float4*>(feat_in + (size_t)src[q] * c_in + ch));
           }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int kb = kb0 + h;
-          if (kb >= n_kb) break;
+          if (kb >= kb_end) break;
           const int ch = kb * kTcKc + c * 4;
           if (has_act && ch < c_in) {
             // deferred epilogue of the producing layer: relu((x + bias) * scale + shift)
@@ -594,6 +609,23 @@ zero_rows_kernel(float* __restrict__ feat, const int* __restrict__ n_rows, int r
     p[e] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+constexpr int kZeroMaxBufs = 16;
+struct ZeroList {
+  float* buf[kZeroMaxBufs];
+  int channels[kZeroMaxBufs];
+  int count;
+};
+
+// blockIdx.y selects the buffer; every buffer clears its first *n_rows rows
+__global__ void __launch_bounds__(256)
+zero_rows_multi_kernel(ZeroList list, const int* __restrict__ n_rows, int row_cap) {
+  const int c = list.channels[blockIdx.y];
+  const long long total = (long long)min(*n_rows, row_cap) * c / 4;
+  float4* p = reinterpret_cast<float4*>(list.buf[blockIdx.y]);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+    p[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void __launch_bounds__(256)
 feature_epilogue_kernel(float* __restrict__ feat, const int* __restrict__ n_rows, int row_cap, int channels,
                         const float* __restrict__ bias, const float* __restrict__ scale,
@@ -674,8 +706,10 @@ static int launch_pairs(const float* feat_in, const int32_t* n_out, int32_t out_
     D3B_CUDA(cudaFuncSetAttribute(spconv_pairs_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  zero_rows_kernel<<<grid_for((long long)out_cap * COUT / 4, 256), 256, 0, stream>>>(feat_out, n_out, out_cap, COUT);
-  D3B_LAUNCH_CHECK();
+  if (!p->out_zeroed) {
+    zero_rows_kernel<<<grid_for((long long)out_cap * COUT / 4, 256), 256, 0, stream>>>(feat_out, n_out, out_cap, COUT);
+    D3B_LAUNCH_CHECK();
+  }
   const int n_kb = (p->c_in + kTcKc - 1) / kTcKc;
   spconv_pairs_kernel<COUT><<<kNumSMs, kPairThreads, Cfg::kSmemBytes, stream>>>(
       feat_in, p->pair_in, p->pair_out, p->pair_count, out_cap, p->k_vol, p->c_in, n_kb, p->weight_packed, p->in_bias,
@@ -720,6 +754,27 @@ int sparse_conv_tc(const float* feat_in, const int32_t* nbr, const uint32_t* til
 }  // namespace d3b
 
 using namespace d3b;
+
+extern "C" int d3b_zero_rows(float* const* bufs, const int32_t* channels, int32_t count, const int32_t* n_rows,
+                             int32_t row_cap, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(count >= 0 && count <= kZeroMaxBufs && row_cap >= 0, "d3b_zero_rows: count %d outside [0, %d]", count, kZeroMaxBufs);
+  if (count == 0 || row_cap == 0) return D3B_OK;
+  D3B_REQUIRE(bufs && channels && n_rows, "d3b_zero_rows: null argument");
+  ZeroList list;
+  int c_max = 0;
+  for (int i = 0; i < count; ++i) {
+    D3B_REQUIRE(bufs[i] && channels[i] > 0 && channels[i] % 4 == 0, "d3b_zero_rows: buffer %d: null or channels %% 4 != 0", i);
+    list.buf[i] = bufs[i];
+    list.channels[i] = channels[i];
+    c_max = channels[i] > c_max ? channels[i] : c_max;
+  }
+  list.count = count;
+  const dim3 grid((unsigned)grid_for((long long)row_cap * c_max / 4, 256, 2), (unsigned)count);
+  zero_rows_multi_kernel<<<grid, 256, 0, stream>>>(list, n_rows, row_cap);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
 
 extern "C" int d3b_feature_epilogue(float* feat, const int32_t* n_rows, int32_t row_cap, int32_t channels,
                                     const float* bias, const float* scale, const float* shift,

@@ -271,7 +271,17 @@ def default_algo(c_in, c_out):
     return _lib.ALGO_TC if tc_supported(c_in, c_out) else _lib.ALGO_SIMT
 
 
-def sparse_conv(feat_in, rb, cw, feat_out, residual=None, in_act=None):
+def zero_rows(bufs, level):
+    """Clear rows [0, n) of every tensor in `bufs` ([cap, C] f32 sharing `level`'s row count) in one launch."""
+    for i in range(0, len(bufs), 16):
+        chunk = bufs[i:i + 16]
+        ptrs = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+        chans = (C.c_int32 * len(chunk))(*[int(t.shape[1]) for t in chunk])
+        st = _lib.lib().d3b_zero_rows(ptrs, chans, len(chunk), level.n.data_ptr(), level.cap, _lib.current_stream())
+        _lib.check(st, "d3b_zero_rows")
+
+
+def sparse_conv(feat_in, rb, cw, feat_out, residual=None, in_act=None, out_zeroed=False):
     """feat_out[:n_out] = epilogue(sum_k feat_in[nbr[k]] @ W[k]).  All device-side.
 
     With cw.algo == ALGO_TC_PAIRS the kernel writes RAW sums (no bias/BN/ReLU/residual of this layer)
@@ -297,6 +307,7 @@ def sparse_conv(feat_in, rb, cw, feat_out, residual=None, in_act=None):
         if rb.pairs is None:
             build_pairs(rb)
         p.pair_in, p.pair_out, p.pair_count = (t.data_ptr() for t in rb.pairs)
+        p.out_zeroed = 1 if out_zeroed else 0
         if in_act is not None:
             b, sc, sh, relu = in_act
             p.in_bias, p.in_scale, p.in_shift, p.in_relu = _lib.ptr(b), _lib.ptr(sc), _lib.ptr(sh), 1 if relu else 0

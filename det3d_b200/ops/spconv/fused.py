@@ -201,6 +201,20 @@ class FusedSparseEncoder:
         main = torch.cuda.current_stream(device)
         ready = {}
         builds = [(rb, build) for _L, rb, build in st["steps"] if build is not None]
+        # the pair-based kernel accumulates with atomics into a zeroed buffer: one dedicated output buffer per layer,
+        # so that all of a resolution's targets can be cleared up front, off the critical path
+        pair_outs = st.setdefault("pair_outs", {})
+        for i, (L, rb, _b) in enumerate(st["steps"]):
+            if L.cw.algo == _lib.ALGO_TC_PAIRS and i not in pair_outs:
+                pair_outs[i] = torch.empty((max(rb.out_level.cap, 1), L.conv.out_channels), dtype=torch.float32, device=device)
+        is_pairs = [L.cw.algo == _lib.ALGO_TC_PAIRS for L, _r, _b in st["steps"]]
+
+        def prepare(rb, build):
+            build(rb, with_pairs=self._wants_pairs(st, rb))
+            bufs = [pair_outs[i] for i, (_L, r2, _b) in enumerate(st["steps"]) if r2 is rb and is_pairs[i]]
+            if bufs:
+                core.zero_rows(bufs, rb.out_level)
+
         if self.overlap_rulebooks and len(builds) > 1:
             side = st.get("side_stream")
             if side is None:
@@ -208,16 +222,16 @@ class FusedSparseEncoder:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 for rb, build in builds:
-                    build(rb, with_pairs=self._wants_pairs(st, rb))
+                    prepare(rb, build)
                     ev = torch.cuda.Event()
                     ev.record(side)
                     ready[id(rb)] = ev
             builds = []
         waited = set()
 
-        for L, rb, build in st["steps"]:
-            if build is not None and builds:   # single-stream order: pairs are compacted inside the neighbour kernel
-                build(rb, with_pairs=self._wants_pairs(st, rb))
+        for i, (L, rb, build) in enumerate(st["steps"]):
+            if build is not None and builds:   # single-stream order
+                prepare(rb, build)
             if id(rb) in ready and id(rb) not in waited:
                 main.wait_event(ready[id(rb)])
                 waited.add(id(rb))
@@ -227,15 +241,16 @@ class FusedSparseEncoder:
                 identity = x
             if not pairs:
                 materialize()            # output-stationary kernels read activated inputs
-            out = self._take(st["pools"], rb.out_level.cap, L.conv.out_channels, (x, identity), device)
             if pairs:
-                core.sparse_conv(x, rb, L.cw, out, in_act=pending)
+                out = pair_outs[i]
+                core.sparse_conv(x, rb, L.cw, out, in_act=pending, out_zeroed=True)
                 pending = (L.cw.bias, L.cw.scale, L.cw.shift, L.cw.relu)
                 x, x_level = out, rb.out_level
                 if L.residual:
                     core.feature_epilogue(x, x_level, *pending[:3], residual=identity, relu=pending[3])
                     pending, identity = None, None
             else:
+                out = self._take(st["pools"], rb.out_level.cap, L.conv.out_channels, (x, identity), device)
                 core.sparse_conv(x, rb, L.cw, out, residual=identity if L.residual else None)
                 if L.residual:
                     identity = None

@@ -158,12 +158,20 @@ typedef struct {
   const float* in_scale;
   const float* in_shift;
   int32_t in_relu;
+  int32_t out_zeroed;            /* nonzero: rows [0, *n_out) of feat_out are already zero (d3b_zero_rows), the
+                                    kernel skips its own clearing launch */
 } d3b_conv_params;
 
 /* Compact the output-stationary map into per-offset pair lists (spconv's classic rulebook form):
  * for every k, the (in_row, out_row) of each valid nbr[k][o], densely packed; pair_count[k] pairs. */
 int d3b_rulebook_pairs(const int32_t* nbr, const int32_t* n_out, int32_t out_cap, int32_t k_vol,
                        int32_t* pair_in, int32_t* pair_out, int32_t* pair_count, void* stream);
+
+/* Clear rows [0, *n_rows) of up to 16 feature buffers that share a row count, in one launch (the accumulation
+ * targets of the D3B_ALGO_TC_PAIRS layers of one resolution).  bufs / channels are HOST arrays of `count` entries;
+ * channels[i] % 4 == 0. */
+int d3b_zero_rows(float* const* bufs, const int32_t* channels, int32_t count, const int32_t* n_rows,
+                  int32_t row_cap, void* stream);
 
 /* In-place epilogue over rows [0, *n_rows): x = relu?((x + bias) * scale + shift + residual). */
 int d3b_feature_epilogue(float* feat, const int32_t* n_rows, int32_t row_cap, int32_t channels,

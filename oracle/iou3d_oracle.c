@@ -359,7 +359,7 @@ void oracle_rrpn_iou_matrix(const float* boxes, int n, const float* query, int k
 
 /* rotate_nms_gpu :453-496 (mask kernel :411-450 + nms_postprocess :110-127).  dets [n,6] = cx,cy,w,l,r,score,
  * `order` = argsort(score)[::-1]; keep[] receives ORIGINAL indices.  near[0] counts tested pairs whose IoU lies
- * within 1e-5 of the threshold (their outcome may differ between sin/cos implementations). */
+ * within 1e-4 of the threshold (their outcome may differ between sin/cos / FMA implementations). */
 int64_t oracle_rrpn_nms(const float* dets, const int32_t* order, int64_t n, float thresh, int64_t* keep, int64_t* near) {
   uint8_t* sup = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
   int64_t nk = 0, nn = 0;
@@ -369,7 +369,7 @@ int64_t oracle_rrpn_nms(const float* dets, const int32_t* order, int64_t n, floa
     keep[nk++] = i;
     for (int64_t _j = _i + 1; _j < n; ++_j) {
       double iou = oracle_rrpn_iou(dets + 6 * i, dets + 6 * order[_j], -1);
-      if (fabs(iou - (double)thresh) < 1e-5) ++nn;
+      if (fabs(iou - (double)thresh) < 1e-4) ++nn;
       if (iou > (double)thresh) sup[_j] = 1;
     }
   }
