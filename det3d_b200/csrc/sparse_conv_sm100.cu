@@ -25,8 +25,8 @@
 // groups take every third slot so three global round trips are in flight per SM (a thread
 // cannot keep loads in flight across fence.proxy.async -- measured: the fence waits for them);
 // the tile's neighbour indices are staged in shared memory once per tile.  Persistent grid
-// (<= one CTA per SM), tile loop with an accumulator full/empty barrier pair; the groups split
-// the epilogue's 16-column chunks.
+// (<= one CTA per SM); four dedicated epilogue warps and two TMEM accumulators, so a tile's drain
+// overlaps the next tile's MMAs (17 warps: 12 gather, 1 MMA, 4 epilogue).
 //
 // Measured bound (ncu, profiles/r1_spconv_tc_v3_ncu.md): the L1/shared-memory data pipe --
 // per slot the tensor core re-reads A_hi and B_hi (3 MMAs x 2 operands), the producers store
@@ -39,11 +39,24 @@
 
 namespace d3b {
 
+// Development aid (never compiled into the product library): -DD3B_TRACE records SM clock stamps of the pipeline
+// roles of CTA 0 so that a slot's life (gather issue -> stage free -> stored -> MMA issued) can be read back.
+#ifdef D3B_TRACE
+__device__ long long g_trace[16 * 1024];
+#define D3B_TRACE_AT(slot, idx)                                                              \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && (slot) < 1024u) g_trace[(slot) * 16 + (idx)] = clock64();         \
+  } while (0)
+#else
+#define D3B_TRACE_AT(slot, idx)
+#endif
+
 constexpr int kTcTileM = 128;
 constexpr int kTcKc = 32;               // channels per stage = one 128-byte swizzle row
 constexpr int kTcGroups = 3;            // gather groups of 4 warps, each producing every 3rd pipeline slot
-constexpr int kTcMmaWarp = 4 * kTcGroups;                 // last warp: TMEM alloc + MMA issue
-constexpr int kTcThreads = 128 * kTcGroups + 32;
+constexpr int kTcMmaWarp = 4 * kTcGroups;                 // TMEM alloc + MMA issue
+constexpr int kTcEpiWarp0 = kTcMmaWarp + 1;               // four epilogue warps (one per TMEM lane quadrant)
+constexpr int kTcThreads = 32 * (kTcEpiWarp0 + 4);        // 544
 constexpr int kABytes = kTcTileM * 128; // one A tile (hi or lo)
 
 // ---- PTX wrappers --------------------------------------------------------------------
@@ -129,7 +142,8 @@ struct TcCfg {
   static constexpr int kBBytes = COUT * 128;                       // one B tile (hi or lo)
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = (COUT >= 128) ? 3 : 4;
-  static constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
+  static constexpr int kAccCols = COUT < 32 ? 32 : COUT;          // columns of one accumulator
+  static constexpr int kTmemCols = 2 * kAccCols;                  // double-buffered across tiles
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers, offsets*/ +
                                     32 * kTcTileM * 4 /*neighbour rows of the tile*/;
 };
@@ -148,9 +162,9 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  const uint32_t accum_full = bar_base + 8u * (2 * Cfg::kStages);
-  const uint32_t tmem_empty = bar_base + 8u * (2 * Cfg::kStages + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 2));
+  auto acc_full = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + b); };        // MMA -> epilogue
+  auto acc_empty = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };   // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
   int* koff_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 128);          // [32] active offsets
   int* nbr_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);           // [32][128] neighbour rows
 
@@ -163,8 +177,10 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
       mbar_init(full_bar(s), 128 + 1);  // the 128 gather threads of one group + the expect_tx arrive
       mbar_init(empty_bar(s), 1);       // tcgen05.commit
     }
-    mbar_init(accum_full, 1);
-    mbar_init(tmem_empty, 128 * kTcGroups);
+    for (uint32_t b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);        // tcgen05.commit of the tile's last MMA
+      mbar_init(acc_empty(b), 128);     // the four epilogue warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kTcMmaWarp) {
@@ -182,7 +198,7 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
   uint32_t tile_it = 0;   // accumulator phase counter
 
   if (warp < kTcMmaWarp) {
-    // ============ gather producers (kTcGroups groups of 4 warps), then epilogue ============
+    // ============ gather producers (kTcGroups groups of 4 warps) ============
     // Group g produces the pipeline slots it with it % kTcGroups == g, so kTcGroups dependent
     // "feature rows -> shared memory" chains are in flight per SM.  A thread must not hold
     // outstanding global loads across fence.proxy.async (the fence waits for them), hence no
@@ -223,7 +239,9 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
         const uint32_t it = it0 + (uint32_t)j;
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
+        if (issues_tma) D3B_TRACE_AT(it, 0);
         mbar_wait(empty_bar(s), ph ^ 1u);
+        if (issues_tma) D3B_TRACE_AT(it, 1);
         uint8_t* stage = smem_gen + (size_t)s * Cfg::kStageBytes;
         if (issues_tma) {
           mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
@@ -243,24 +261,74 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
           *reinterpret_cast<float4*>(stage + off) = hi;
           *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
         }
+        if (issues_tma) D3B_TRACE_AT(it, 2);
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(s));
+        if (issues_tma) D3B_TRACE_AT(it, 3);
       }
       it0 += (uint32_t)n_slots;
 
-      // ---- epilogue: TMEM -> registers -> fused BN/bias/residual/ReLU -> global; the groups
-      //      split the 16-column chunks between them ----
-      const bool any = n_slots != 0;
-      const int o = row0 + wq * 32 + lane;
+    }
+  } else if (warp == kTcMmaWarp) {
+    // ===================== MMA issuer (one elected lane) =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(kTcTileM, COUT);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const unsigned int mask = tile_mask[tile];
+      if (mask == 0) continue;
+      const int n_slots = __popc(mask) * n_kb;
+      const uint32_t buf = tile_it & 1u;                   // accumulators alternate: the epilogue of tile t drains
+      mbar_wait(acc_empty(buf), ((tile_it >> 1) & 1u) ^ 1u);   // one while the MMAs of tile t+1 fill the other
+      tc_fence_after();
+      const uint32_t d_addr = tmem_d + buf * Cfg::kAccCols;
+      uint32_t accumulate = 0;
+      for (int j = 0; j < n_slots; ++j, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1u;
+        if (lane == 0) D3B_TRACE_AT(it, 4);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) D3B_TRACE_AT(it, 5);
+        if (lane == 0) {
+          const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_lo + kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int kk = 0; kk < kTcKc / 8; ++kk) {
+            const uint32_t adv = kk * 32;  // 8 tf32 = 32 bytes along K inside the swizzle row
+            tc_mma_tf32(d_addr, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, accumulate);
+            tc_mma_tf32(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
+            tc_mma_tf32(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
+            accumulate = 1u;
+          }
+          tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+        }
+        __syncwarp();
+        accumulate = 1u;
+      }
+      if (lane == 0) tc_commit(acc_full(buf));
+      __syncwarp();
+      ++tile_it;
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> fused bias/BN/residual/ReLU -> global =====================
+    // Dedicated warps + two accumulators: the tile's drain (and the pipeline refill of the next tile) used to cost
+    // ~12k of ~52k cycles per 128-row tile of a dense 128->128 layer with the MMA pipe idle (clock-stamp trace).
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const bool any = tile_mask[tile] != 0u;
+      const int o = tile * kTcTileM + quad * 32 + lane;
+      const uint32_t buf = tile_it & 1u;
       if (any) {
-        mbar_wait(accum_full, tile_it & 1u);
+        mbar_wait(acc_full(buf), (tile_it >> 1) & 1u);
         tc_fence_after();
       }
 #pragma unroll 1
-      for (int c0 = group * 16; c0 < COUT; c0 += 16 * kTcGroups) {
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
         uint32_t r[16];
         if (any) {
-          tc_ld16(tmem_d + ((uint32_t)(wq * 32) << 16) + c0, r);
+          tc_ld16(tmem_d + buf * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16) + c0, r);
         } else {
 #pragma unroll
           for (int q = 0; q < 16; ++q) r[q] = 0u;
@@ -294,47 +362,9 @@ spconv_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr,
       }
       if (any) {
         tc_fence_before();
-        mbar_arrive(tmem_empty);   // accumulator drained: the MMA thread may start the next tile
+        mbar_arrive(acc_empty(buf));   // accumulator drained: the MMA thread may reuse it
         ++tile_it;
       }
-    }
-  } else {
-    // ===================== MMA issuer (one elected lane of the last warp) =====================
-    constexpr uint32_t idesc = umma_idesc_tf32(kTcTileM, COUT);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const unsigned int mask = tile_mask[tile];
-      if (mask == 0) continue;
-      const int n_slots = __popc(mask) * n_kb;
-      mbar_wait(tmem_empty, (tile_it & 1u) ^ 1u);
-      tc_fence_after();
-      uint32_t accumulate = 0;
-      for (int j = 0; j < n_slots; ++j, ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1u;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
-          const uint32_t a_lo = a_hi + kABytes;
-          const uint32_t b_hi = a_lo + kABytes;
-          const uint32_t b_lo = b_hi + Cfg::kBBytes;
-#pragma unroll
-          for (int kk = 0; kk < kTcKc / 8; ++kk) {
-            const uint32_t adv = kk * 32;  // 8 tf32 = 32 bytes along K inside the swizzle row
-            tc_mma_tf32(tmem_d, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, accumulate);
-            tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
-            tc_mma_tf32(tmem_d, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
-            accumulate = 1u;
-          }
-          tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
-        }
-        __syncwarp();
-        accumulate = 1u;
-      }
-      if (lane == 0) tc_commit(accum_full);
-      __syncwarp();
-      ++tile_it;
     }
   }
 
@@ -370,6 +400,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// stages + barriers/offsets (256) + work-item tables (512) + producer-epilogue parameters (3 x 128 floats) + the
+// epilogue's four padded 32x36 transpose tiles
+template <int COUT>
+constexpr int kPairSmem = TcCfg<COUT>::kStages * TcCfg<COUT>::kStageBytes + 1024 + 256 + 512 + 3 * 128 * 4 + 4 * 32 * 36 * 4;
+
 template <int COUT>
 __global__ void __launch_bounds__(kPairThreads, 1)
 spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ pair_in,
@@ -391,6 +426,8 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
   int* chunk_prefix = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);   // [k_vol + 1]
   int* count_s = chunk_prefix + 40;                                                                // [k_vol]
+  float* act_s = reinterpret_cast<float*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256 + 512);        // [3][128] bias, scale, shift
+  float* epi_stage = act_s + 3 * 128;                                                                     // [4][32*36]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -403,14 +440,29 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
       mbar_init(acc_empty(b), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    int run = 0;
-    for (int k = 0; k < k_vol; ++k) {
-      const int cnt = min(pair_count[k], out_cap);
-      count_s[k] = cnt;
-      chunk_prefix[k] = run;
-      run += (cnt + kTcTileM - 1) / kTcTileM;
+  }
+  // the producing layer's deferred epilogue, staged once (identity where a pointer is NULL)
+  for (int ch = threadIdx.x; ch < 128; ch += blockDim.x) {
+    const bool in = ch < c_in;
+    act_s[ch] = (in && in_bias) ? in_bias[ch] : 0.f;
+    act_s[128 + ch] = (in && in_scale) ? in_scale[ch] : 1.f;
+    act_s[256 + ch] = (in && in_scale) ? in_shift[ch] : 0.f;
+  }
+  if (warp == 0) {
+    // work-item table: one lane per offset (k_vol <= 32), a warp scan instead of k_vol dependent global loads
+    const int cnt = lane < k_vol ? min(pair_count[lane], out_cap) : 0;
+    const int chunks = (cnt + kTcTileM - 1) / kTcTileM;
+    int incl = chunks;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
     }
-    chunk_prefix[k_vol] = run;
+    if (lane < k_vol) {
+      count_s[lane] = cnt;
+      chunk_prefix[lane] = incl - chunks;
+    }
+    if (lane == k_vol - 1) chunk_prefix[k_vol] = incl;
   }
   if (warp == kPairMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -424,10 +476,11 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
   const uint32_t tmem_d = *tmem_slot;
   const int n_items = chunk_prefix[k_vol];
 
-  auto item_k = [&](int item) {          // offset of a work item (k_vol <= 32 entries: linear walk)
-    int k = 0;
-    while (k + 1 < k_vol && chunk_prefix[k + 1] <= item) ++k;
-    return k;
+  // offset of a work item = number of offsets whose first item precedes it; one LDS + a ballot instead of a
+  // k_vol-long dependent walk (every caller is warp-uniform)
+  auto item_k = [&](int item) {
+    const bool before = lane + 1 < k_vol && chunk_prefix[lane + 1] <= item;
+    return __popc(__ballot_sync(0xffffffffu, before));
   };
 
   if (warp < kPairMmaWarp) {
@@ -439,34 +492,49 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
     const int g = lane >> 3, c = lane & 7;
     const bool issues_tma = (wq == 0 && lane == 0);
     const bool has_act = in_scale != nullptr || in_bias != nullptr || in_relu;
-    uint32_t seq = 0;                     // CTA-local item ordinal
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++seq) {
-      // Which 32-channel slices of this item the group fills.  A group waits for a stage on the parity of its
-      // empty barrier, which is only unambiguous if the previous use of that stage is known to have been consumed;
-      // a group's own earlier slots provide that guarantee when they are at most kStages - 1 slots behind, so the
-      // split keeps every group's consecutive slots close: items alternate between the groups for n_kb <= 2,
-      // both groups take half of every item for n_kb == 4, and the (unused by the named configs) n_kb == 3 case
-      // runs on one group.
-      int kb_begin = 0, kb_end = n_kb;
-      if (n_kb == 4) {
-        kb_begin = 2 * group;
-        kb_end = kb_begin + 2;
-      } else if (n_kb == 3) {
-        if (group != 0) continue;
-      } else if ((int)(seq % kPairGroups) != group) {
-        continue;
-      }
+    // Which items this group works on, and which 32-channel slices of them.  A group waits for a stage on the
+    // parity of its empty barrier, which is only unambiguous if the previous use of that stage is known to have
+    // been consumed; a group's own earlier slots provide that guarantee when they are at most kStages - 1 slots
+    // behind, so the split keeps every group's consecutive slots close: items alternate between the groups for
+    // n_kb <= 2, both groups take half of every item for n_kb == 4, and the (unused by the named configs)
+    // n_kb == 3 case runs on one group.
+    auto mine = [&](uint32_t sq) {
+      return n_kb == 4 ? true : (n_kb == 3 ? group == 0 : (int)(sq % kPairGroups) == group);
+    };
+    auto load_src = [&](int item, int (&dst)[8]) {   // the 8 input-row indices this thread gathers for `item`
       const int k = item_k(item);
       const int first = (item - chunk_prefix[k]) * kTcTileM;
       const int cnt = count_s[k];
       const int* pin = pair_in + (size_t)k * out_cap + first;
-      int src[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int row = wq * 32 + 4 * q + g;
-        src[q] = first + row < cnt ? __ldg(pin + row) : -1;
+        dst[q] = first + row < cnt ? __ldg(pin + row) : -1;
       }
+    };
+    int item = blockIdx.x;
+    uint32_t seq = 0;                     // CTA-local item ordinal
+    while (item < n_items && !mine(seq)) { item += gridDim.x; ++seq; }
+    int src_next[8];
+    if (item < n_items) load_src(item, src_next);
+    while (item < n_items) {
+      int src[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) src[q] = src_next[q];
+      int next_item = item + gridDim.x;
+      uint32_t next_seq = seq + 1;
+      while (next_item < n_items && !mine(next_seq)) { next_item += gridDim.x; ++next_seq; }
+      bool prefetched = false;
+      int kb_begin = 0, kb_end = n_kb;
+      if (n_kb == 4) {
+        kb_begin = 2 * group;
+        kb_end = kb_begin + 2;
+      }
+      const int k = item_k(item);
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += 2) {
+        // the indices of this group's NEXT item travel together with this round's feature rows: one global round
+        // trip per item instead of two (they complete before the fence.proxy.async below would wait for them anyway)
+        if (!prefetched && next_item < n_items) { load_src(next_item, src_next); prefetched = true; }
         float4 v[2][8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -485,9 +553,9 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
           const int ch = kb * kTcKc + c * 4;
           if (has_act && ch < c_in) {
             // deferred epilogue of the producing layer: relu((x + bias) * scale + shift)
-            const float4 b4 = in_bias ? __ldg(reinterpret_cast<const float4*>(in_bias + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 s4 = in_scale ? __ldg(reinterpret_cast<const float4*>(in_scale + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float4 t4 = in_scale ? __ldg(reinterpret_cast<const float4*>(in_shift + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b4 = *reinterpret_cast<const float4*>(act_s + ch);
+            const float4 s4 = *reinterpret_cast<const float4*>(act_s + 128 + ch);
+            const float4 t4 = *reinterpret_cast<const float4*>(act_s + 256 + ch);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               if (src[q] >= 0) {
@@ -504,7 +572,9 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
           const uint32_t it = seq * (uint32_t)n_kb + (uint32_t)kb;
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
+          if (issues_tma) D3B_TRACE_AT(it, 0);
           mbar_wait(empty_bar(s), ph ^ 1u);
+          if (issues_tma) D3B_TRACE_AT(it, 1);
           uint8_t* stage = smem_gen + (size_t)s * Cfg::kStageBytes;
           if (issues_tma) {
             mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
@@ -523,10 +593,14 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
             *reinterpret_cast<float4*>(stage + off) = hi;
             *reinterpret_cast<float4*>(stage + kABytes + off) = lo;
           }
+          if (issues_tma) D3B_TRACE_AT(it, 2);
           fence_proxy_async();
           mbar_arrive(full_bar(s));
+          if (issues_tma) D3B_TRACE_AT(it, 3);
         }
       }
+      item = next_item;
+      seq = next_seq;
     }
   } else if (warp == kPairMmaWarp) {
     // ===================== MMA issuer =====================
@@ -541,8 +615,10 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
       for (int kb = 0; kb < n_kb; ++kb, ++it) {
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
+        if (lane == 0) D3B_TRACE_AT(it, 4);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (lane == 0) D3B_TRACE_AT(it, 5);
         if (lane == 0) {
           const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
           const uint32_t a_lo = a_hi + kABytes;
@@ -574,22 +650,40 @@ spconv_pairs_kernel(const float* __restrict__ feat_in, const int* __restrict__ p
       const int row = first + quad * 32 + lane;
       const int o = row < count_s[k] ? __ldg(pair_out + (size_t)k * out_cap + row) : -1;
       const uint32_t buf = seq & 1u;
+      if (quad == 0 && lane == 0) D3B_TRACE_AT(seq * (uint32_t)n_kb, 6);
       mbar_wait(acc_full(buf), (seq >> 1) & 1u);
       tc_fence_after();
+      if (quad == 0 && lane == 0) D3B_TRACE_AT(seq * (uint32_t)n_kb, 7);
+      // TMEM hands every lane one row; a warp-wide red of that layout touches 32 different 128-byte lines with 16
+      // bytes each (measured 2.0 us per 128 x 64 item per SM).  Transposing each 32-column chunk through a padded
+      // shared-memory tile lets eight lanes cover one row's full 128-byte line per instruction: 0.94 us per item.
+      constexpr int kCw = COUT < 32 ? COUT : 32;     // columns per chunk
+      constexpr int kLpr = kCw / 4;                  // lanes per row
+      constexpr int kRpi = 32 / kLpr;                // rows per red instruction
+      float* stg = epi_stage + quad * (32 * 36);     // row stride 36 floats: 16-byte aligned rows, conflict-free
+                                                     // for 128-bit stores (lane = row) and loads (8 lanes per row)
 #pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(tmem_d + buf * kAccCols + ((uint32_t)(quad * 32) << 16) + c0, r);
-        if (o >= 0) {
-          float* dst = feat_out + (size_t)o * COUT + c0;
+      for (int c0 = 0; c0 < COUT; c0 += kCw) {
+        uint32_t r[kCw];
 #pragma unroll
-          for (int q = 0; q < 16; q += 4)
-            red_add_v4(dst + q, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
-                       __uint_as_float(r[q + 3]));
+        for (int h = 0; h < kCw; h += 16) tc_ld16(tmem_d + buf * kAccCols + ((uint32_t)(quad * 32) << 16) + c0 + h,
+                                                  *reinterpret_cast<uint32_t(*)[16]>(&r[h]));
+        __syncwarp();                                // the previous chunk has been read out of the tile
+#pragma unroll
+        for (int q = 0; q < kCw; q += 4)
+          *reinterpret_cast<uint4*>(stg + lane * 36 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += kRpi) {
+          const int rr = j + lane / kLpr;
+          const int orow = __shfl_sync(0xffffffffu, o, rr);
+          const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + (lane % kLpr) * 4);
+          if (orow >= 0) red_add_v4(feat_out + (size_t)orow * COUT + c0 + (lane % kLpr) * 4, x.x, x.y, x.z, x.w);
         }
       }
       tc_fence_before();
       mbar_arrive(acc_empty(buf));
+      if (quad == 0 && lane == 0) D3B_TRACE_AT(seq * (uint32_t)n_kb, 8);
     }
   }
 
@@ -703,7 +797,7 @@ static int launch_pairs(const float* feat_in, const int32_t* n_out, int32_t out_
   using Cfg = TcCfg<COUT>;
   static bool attr_set = false;
   if (!attr_set) {
-    D3B_CUDA(cudaFuncSetAttribute(spconv_pairs_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    D3B_CUDA(cudaFuncSetAttribute(spconv_pairs_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem<COUT>));
     attr_set = true;
   }
   if (!p->out_zeroed) {
@@ -711,7 +805,7 @@ static int launch_pairs(const float* feat_in, const int32_t* n_out, int32_t out_
     D3B_LAUNCH_CHECK();
   }
   const int n_kb = (p->c_in + kTcKc - 1) / kTcKc;
-  spconv_pairs_kernel<COUT><<<kNumSMs, kPairThreads, Cfg::kSmemBytes, stream>>>(
+  spconv_pairs_kernel<COUT><<<kNumSMs, kPairThreads, kPairSmem<COUT>, stream>>>(
       feat_in, p->pair_in, p->pair_out, p->pair_count, out_cap, p->k_vol, p->c_in, n_kb, p->weight_packed, p->in_bias,
       p->in_scale, p->in_shift, p->in_relu, feat_out);
   D3B_LAUNCH_CHECK();
@@ -754,6 +848,16 @@ int sparse_conv_tc(const float* feat_in, const int32_t* nbr, const uint32_t* til
 }  // namespace d3b
 
 using namespace d3b;
+
+#ifdef D3B_TRACE
+extern "C" int d3b_debug_trace(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, d3b::g_trace, (size_t)n * 8);
+}
+extern "C" int d3b_debug_trace_clear(void) {
+  static long long zeros[16 * 1024];
+  return (int)cudaMemcpyToSymbol(d3b::g_trace, zeros, sizeof(zeros));
+}
+#endif
 
 extern "C" int d3b_zero_rows(float* const* bufs, const int32_t* channels, int32_t count, const int32_t* n_rows,
                              int32_t row_cap, void* stream_) {
