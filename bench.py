@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -78,13 +78,20 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
+
+    def mark(self):
+        """Start of the load window: samples read before this moment are dropped."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r for r in self.rows if r[-1] >= t0] or self.rows[-3:]
+        self.rows = rows
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -231,6 +238,9 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for s in range(max(args.warmup, 3)):
         step_device(s)
         step_e2e(s)
@@ -240,12 +250,9 @@ def main():
         pts = resident[ids[0]] if B == 1 else torch.cat([resident[i] for i in ids])
         return all_gather_detections(pipe.pack(pipe.forward_device(pts, offsets)))
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()                      # clocks are sampled from here to the end of the per-kernel pass (same load)
     ms = timed(step_device, args.steps)
     ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel pass (eager launches of the SAME kernels, CUDA events around every
     #      d3b_sparse_conv launch on the launching stream): launch count + roofline numerators ----
@@ -255,6 +262,7 @@ def main():
     timed(step_eager, n_prof, conv_events)
     launches_per_step = (_lib.launch_count() - launches0) / n_prof
     torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
 
     peaks = {}
     try:
@@ -262,33 +270,53 @@ def main():
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    tc_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0       # kind::tf32 runs at half the bf16 rate
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    traffic = {}
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except OSError:
+        pass
     enc = pipe.model.backbone.fused().accounting()             # algorithmic bytes / flops of the last step
     n_enc = len(enc["layers"])
     per_step = len(conv_events) // n_prof
-    enc_ms = sum(a.elapsed_time(b) for i, (a, b) in enumerate(conv_events) if i % per_step < n_enc) / n_prof
-    bev_ms = sum(a.elapsed_time(b) for i, (a, b) in enumerate(conv_events) if i % per_step >= n_enc) / n_prof
+    ev_ms = [a.elapsed_time(b) for a, b in conv_events]
+    enc_ms = sum(t for i, t in enumerate(ev_ms) if i % per_step < n_enc) / n_prof
+    bev_ms = sum(t for i, t in enumerate(ev_ms) if i % per_step >= n_enc) / n_prof
     ms_step = ms / args.steps
-    achieved = enc["bytes"] / (enc_ms * 1e-3) / 1e9 if enc_ms > 0 else 0.0
-    roofline = {"kernel": "d3b spconv_tc_kernel / spconv_simt_kernel: sparse middle encoder, %d launches/step" % n_enc,
-                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": enc["bytes"],
-                "flops_per_step": enc["flops"], "kernel_ms_per_step": enc_ms,
-                "achieved_tflops": enc["flops"] / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else 0.0,
-                "share_of_step": enc_ms / ms_step, "timing": "CUDA events around each launch, eager pass of %d steps" % n_prof}
+    timing = "CUDA events around each launch on the launching stream, eager pass of %d steps" % n_prof
+    enc_gbs = enc["bytes"] / (enc_ms * 1e-3) / 1e9 if enc_ms > 0 else 0.0
+    roofline_encoder = {
+        "kernel": "d3b::spconv_pairs_kernel (+ SIMT first layer): sparse middle encoder, %d launches/step" % n_enc,
+        "bound": "hbm", "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": enc_gbs / hbm_peak,
+        "traffic": traffic.get("encoder_dram_bytes_per_step"), "peak_source": peak_src,
+        "algorithmic_bytes_per_step": enc["bytes"], "flops_per_step": enc["flops"], "kernel_ms_per_step": enc_ms,
+        "share_of_step": enc_ms / ms_step, "timing": timing,
+        "note": "below the ridge by construction (2..32 flop/B); measured bound: L2 fp32 atomic (red.v4) issue rate and "
+                "dependent L2 round trips, not DRAM (DESIGN.md 3.3)"}
+    roofline = roofline_encoder
     extra = {}
     if per_step > n_enc:
+        # dominant kernel of the step: spconv_tc_kernel<128> on the dense BEV grid, the six 3x3 128->128 RPN layers
         hw = B * 200 * 176
+        flops_3x3 = 2 * hw * 9 * 128 * 128
+        bytes_3x3 = hw * 128 * 4 * 2 + 9 * 128 * 128 * 4
+        ms_3x3 = sum(t for i, t in enumerate(ev_ms) if n_enc <= i % per_step < n_enc + 6) / (6 * n_prof)
+        tf = flops_3x3 / (ms_3x3 * 1e-3) / 1e12 if ms_3x3 > 0 else 0.0
         bev_flops = sum(2 * hw * k * ci * co for (k, ci, co) in [(9, 128, 128)] * 6 + [(1, 128, 128), (1, 128, 32)])
-        bev_tf = bev_flops / (bev_ms * 1e-3) / 1e12 if bev_ms > 0 else 0.0
-        extra["roofline_bev"] = {"kernel": "d3b spconv_tc_kernel on the dense BEV grid (RPN 6x conv3x3 + 1x1 deblock + fused heads), "
-                                           "%d launches/step" % (per_step - n_enc),
-                                 "bound": "tensor", "achieved": bev_tf, "peak": tc_peak, "unit": "TFLOP/s",
-                                 "frac": bev_tf / tc_peak, "traffic": None,
-                                 "note": "fp32-equivalent flops; the kernel issues 3 TF32 MMAs per product (3xTF32), "
-                                         "so tensor-pipe work is 3x this; peak = measured bf16 burst / 2",
-                                 "flops_per_step": bev_flops, "kernel_ms_per_step": bev_ms, "share_of_step": bev_ms / ms_step}
+        roofline = {
+            "kernel": "d3b::spconv_tc_kernel<128>: dense BEV conv3x3 128->128 (RPN), 6 of the %d BEV launches/step"
+                      % (per_step - n_enc),
+            "bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
+            "traffic": traffic.get("bev3x3_dram_bytes_per_launch"), "peak_source": peak_src,
+            "algorithmic_flops_per_launch": flops_3x3, "algorithmic_bytes_per_launch": bytes_3x3,
+            "launch_ms": ms_3x3, "launches_per_step": 6, "share_of_step": 6 * ms_3x3 / ms_step, "timing": timing,
+            "note": "fp32-equivalent flops (the reference runs this layer as fp32 cuDNN). The kernel reaches fp32 accuracy "
+                    "with 3 TF32 MMAs per product (3xTF32) on a pipe whose TF32 rate is half the bf16 rate, so the "
+                    "ceiling of this algorithm is peak/6 and tensor-pipe utilisation is 6 x frac = %.2f" % (6 * tf / bf16_peak),
+            "bev_stack": {"launches_per_step": per_step - n_enc, "flops_per_step": bev_flops, "kernel_ms_per_step": bev_ms,
+                          "share_of_step": bev_ms / ms_step}}
+        extra["roofline_encoder"] = roofline_encoder
 
     if rank != 0:
         if world > 1:

@@ -311,6 +311,15 @@ __device__ __forceinline__ double quad_area(const Quad& q) {
 }
 
 // nms_cpu.h:103-158: skip unless hulls overlap; overlap = inter / union; suppress when >= thresh.
+// the polygon part of the test, for a pair whose hulls overlap (standup_iou > 0)
+__device__ __forceinline__ bool clip_suppresses_xywlr(const Quad& a, const Quad& b, float thresh) {
+  const double inter = quad_intersection_area(a, b);
+  if (!(inter > 0.0)) return false;
+  const double uni = quad_area(a) + quad_area(b) - inter;
+  if (!(uni > 0.0)) return false;
+  return (float)(inter / uni) >= thresh;
+}
+
 __device__ __forceinline__ bool suppresses_xywlr(const Quad& a, const Quad& b, float thresh, float* iou_out) {
   if (iou_out) *iou_out = 0.0f;
   if (standup_iou(a, b) <= 0.0f) return false;
@@ -488,6 +497,11 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
   __shared__ Disc dcol[FMT == 0 ? kNmsBlock : 1];
   __shared__ Quad qcol[FMT == 1 ? kNmsBlock : 1];
   __shared__ Quad qrow[FMT == 1 ? kNmsRowsPerCta : 1];
+  __shared__ unsigned short s_list[FMT == 1 ? kNmsRowsPerCta * kNmsBlock : 1];
+  __shared__ unsigned int s_bits[2 * kNmsRowsPerCta];
+  __shared__ int s_count;
+  if (threadIdx.x < 2 * kNmsRowsPerCta) s_bits[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) s_count = 0;
   const int tx = threadIdx.x & 63;        // column inside the block
   const int ty = threadIdx.x >> 6;        // 0..3
   unsigned int* mask32 = reinterpret_cast<unsigned int*>(mask);
@@ -519,6 +533,30 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if (FMT == 1) qrow[r] = quad_of_xywlr(src);
     }
     __syncthreads();
+    if (FMT == 1) {
+      // rotate_nms_cc pairs: the hull gate (fp32, a few instructions) passes only a few percent of the pairs, the
+      // fp64 polygon clip behind it costs thousands of instructions.  Testing the gate for all 16 x 64 pairs first and
+      // compacting the survivors keeps every lane busy in the expensive part instead of one or two lanes per warp.
+      for (int rr = ty; rr < kNmsRowsPerCta; rr += 4) {
+        const int cur = row_first + rr;
+        const bool active = cur < n && tx < col_size && (row != col || tx > slice * kNmsRowsPerCta + rr);
+        if (active && standup_iou(qrow[rr], qcol[tx]) > 0.0f) s_list[atomicAdd(&s_count, 1)] = (unsigned short)(rr * 64 + tx);
+      }
+      __syncthreads();
+      const int n_pairs = s_count;
+      for (int e = threadIdx.x; e < n_pairs; e += blockDim.x) {
+        const int rr = s_list[e] >> 6, cc = s_list[e] & 63;
+        if (clip_suppresses_xywlr(qrow[rr], qcol[cc], thresh)) atomicOr(&s_bits[rr * 2 + (cc >> 5)], 1u << (cc & 31));
+      }
+      __syncthreads();
+      if (threadIdx.x < 2 * kNmsRowsPerCta) {
+        const int rr = threadIdx.x >> 1;
+        if (row_first + rr < n) mask32[((size_t)(row_first + rr) * col_blocks + col) * 2 + (threadIdx.x & 1)] = s_bits[threadIdx.x];
+        s_bits[threadIdx.x] = 0u;
+      }
+      if (threadIdx.x == 0) s_count = 0;
+      continue;                            // the loop-top __syncthreads orders the reset before the next item
+    }
 #pragma unroll 1
     for (int rr = ty; rr < kNmsRowsPerCta; rr += 4) {
       const int cur = row_first + rr;      // warp-uniform

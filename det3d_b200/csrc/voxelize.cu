@@ -13,7 +13,7 @@
 //
 // Four kernels, no sort:
 //   A  vox_insert : cell -> open-addressing hash slot, atomicMin(first point)
-//   B  vox_rank   : one CTA per cloud scans "is first point" flags in input
+//   B  vox_chunk_count / vox_chunk_scan / vox_assign : scan of the "is first point" flags in input
 //                   order -> voxel ids, the cut-off point i*, voxel count
 //   C  vox_lists  : every surviving point cascades its index through the
 //                   voxel's max_points-long sorted list with atomicMin
@@ -38,6 +38,7 @@ struct VoxParams {
   int grid[3];
   int ndim, max_points, max_voxels, batch;
   int off[kMaxBatch + 1];
+  int chunk_off[kMaxBatch + 1];   // rank chunks (1024 points) of the clouds, prefix
 };
 
 __device__ __forceinline__ int cloud_of(const VoxParams& p, int i) {
@@ -78,43 +79,69 @@ vox_insert(const VoxParams p, const float* __restrict__ points, unsigned long lo
   }
 }
 
-// ---- B: rank voxels by first point (one CTA per cloud) -------------------------
-// Each thread owns kRankItems consecutive points per pass so the two dependent loads
-// (pslot -> first) of a whole 8k-point chunk are in flight together.
-constexpr int kRankItems = 8;
+// ---- B: rank voxels by first point ------------------------------------------------
+// voxel id = number of "first points" that precede the voxel's own first point in input order: an exclusive scan
+// of the is-first flags over the cloud.  One CTA per cloud is bound by a single SM's load/store path (measured
+// 28 us for 20k points), so the scan is split the classic way: per-1024-point chunk counts (grid) -> scan of the
+// chunk counts (one CTA per cloud, a few dozen values) -> chunk-local scan + offset (grid).
+constexpr int kRankChunk = 1024;          // points per chunk = 256 threads x 4 consecutive points
 
+__device__ __forceinline__ int chunk_cloud(const VoxParams& p, int g) {
+  int b = 0;
+  while (b + 1 < p.batch && g >= p.chunk_off[b + 1]) ++b;
+  return b;
+}
+
+// is-first flags of the 4 points owned by this thread (bit j) and their hash slots
+__device__ __forceinline__ unsigned int rank_flags(const VoxParams& p, const int* __restrict__ first,
+                                                   const int* __restrict__ pslot, int i0, int end, int (&slot)[4]) {
+  int fst[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) slot[j] = (i0 + j < end) ? pslot[i0 + j] : -1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) fst[j] = slot[j] >= 0 ? first[slot[j]] : -1;
+  unsigned int flags = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) flags |= (unsigned int)(slot[j] >= 0 && fst[j] == i0 + j) << j;
+  return flags;
+}
+
+__global__ void __launch_bounds__(256)
+vox_chunk_count(const VoxParams p, const int* __restrict__ first, const int* __restrict__ pslot,
+                int* __restrict__ chunk_cnt) {
+  __shared__ int warp_sums[8];
+  const int g = blockIdx.x, b = chunk_cloud(p, g);
+  const int i0 = p.off[b] + (g - p.chunk_off[b]) * kRankChunk + threadIdx.x * 4;
+  int slot[4];
+  int local = __popc(rank_flags(p, first, pslot, i0, p.off[b + 1], slot));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += warp_sums[w];
+    chunk_cnt[g] = t;
+  }
+}
+
+// one CTA per cloud: exclusive scan of its chunk counts, voxel count, default cut-off
 __global__ void __launch_bounds__(1024)
-vox_rank(const VoxParams p, const int* __restrict__ first, const int* __restrict__ pslot,
-         int* __restrict__ vid, int* __restrict__ vslot, int* __restrict__ cut,
-         int* __restrict__ counts) {
+vox_chunk_scan(const VoxParams p, const int* __restrict__ chunk_cnt, int* __restrict__ chunk_base,
+               int* __restrict__ cut, int* __restrict__ counts) {
   __shared__ int warp_sums[32];
   __shared__ int running;
-  __shared__ int cut_s;
-  const int b = blockIdx.x;
-  const int beg = p.off[b], end = p.off[b + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { running = 0; cut_s = end; }
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g0 = p.chunk_off[b], g1 = p.chunk_off[b + 1];
+  if (threadIdx.x == 0) running = 0;
   __syncthreads();
-  for (int base = beg; base < end; base += blockDim.x * kRankItems) {
-    const int i0 = base + threadIdx.x * kRankItems;
-    int slot[kRankItems], fst[kRankItems];
-#pragma unroll
-    for (int j = 0; j < kRankItems; ++j) slot[j] = (i0 + j < end) ? pslot[i0 + j] : -1;
-#pragma unroll
-    for (int j = 0; j < kRankItems; ++j) fst[j] = slot[j] >= 0 ? first[slot[j]] : -1;
-    int local = 0;
-    unsigned int flags = 0;
-#pragma unroll
-    for (int j = 0; j < kRankItems; ++j) {
-      const int f = (slot[j] >= 0 && fst[j] == i0 + j) ? 1 : 0;
-      flags |= (unsigned int)f << j;
-      local += f;
-    }
-    // block-wide exclusive scan of the per-thread counts
-    int incl = local;
+  for (int base = g0; base < g1; base += blockDim.x) {
+    const int g = base + threadIdx.x;
+    const int v = g < g1 ? chunk_cnt[g] : 0;
+    int incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
     if (lane == 31) warp_sums[warp] = incl;
@@ -123,34 +150,56 @@ vox_rank(const VoxParams p, const int* __restrict__ first, const int* __restrict
       int w = warp_sums[lane];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, w, d);
+        const int t = __shfl_up_sync(0xffffffffu, w, d);
         if (lane >= d) w += t;
       }
-      warp_sums[lane] = w;  // inclusive over warps
+      warp_sums[lane] = w;
     }
     __syncthreads();
-    const int warp_off = warp == 0 ? 0 : warp_sums[warp - 1];
-    const int chunk_total = warp_sums[31];
-    int r = running + warp_off + incl - local;  // exclusive rank of this thread's first flagged point
-#pragma unroll
-    for (int j = 0; j < kRankItems; ++j) {
-      if (!((flags >> j) & 1u)) continue;
-      if (r < p.max_voxels) {
-        vid[slot[j]] = r;
-        vslot[b * p.max_voxels + r] = slot[j];
-      } else {
-        vid[slot[j]] = -1;
-        if (r == p.max_voxels) cut_s = i0 + j;  // the reference `break` fires here
-      }
-      ++r;
-    }
+    if (g < g1) chunk_base[g] = running + (warp == 0 ? 0 : warp_sums[warp - 1]) + incl - v;
+    const int total = warp_sums[31];
     __syncthreads();
-    if (threadIdx.x == 0) running += chunk_total;
+    if (threadIdx.x == 0) running += total;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     counts[b] = running < p.max_voxels ? running : p.max_voxels;
-    cut[b] = cut_s;
+    cut[b] = p.off[b + 1];               // vox_assign lowers it to the point where the reference `break` fires
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vox_assign(const VoxParams p, const int* __restrict__ first, const int* __restrict__ pslot,
+           const int* __restrict__ chunk_base, int* __restrict__ vid, int* __restrict__ vslot, int* __restrict__ cut) {
+  __shared__ int warp_sums[8];
+  const int g = blockIdx.x, b = chunk_cloud(p, g);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = p.off[b] + (g - p.chunk_off[b]) * kRankChunk + threadIdx.x * 4;
+  int slot[4];
+  const unsigned int flags = rank_flags(p, first, pslot, i0, p.off[b + 1], slot);
+  const int local = __popc(flags);
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int warp_off = 0;
+  for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
+  int r = chunk_base[g] + warp_off + incl - local;   // exclusive rank of this thread's first flagged point
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!((flags >> j) & 1u)) continue;
+    if (r < p.max_voxels) {
+      vid[slot[j]] = r;
+      vslot[b * p.max_voxels + r] = slot[j];
+    } else {
+      vid[slot[j]] = -1;
+      if (r == p.max_voxels) cut[b] = i0 + j;   // the reference `break` fires here
+    }
+    ++r;
   }
 }
 
@@ -240,6 +289,8 @@ struct VoxWorkspace {
   int* pslot;   // [n_total]
   int* vslot;   // [B*MV]
   int* cut;     // [B]
+  int* chunk_cnt;   // [chunks] is-first points per 1024-point chunk
+  int* chunk_base;  // [chunks] exclusive scan of the above within the cloud
   size_t cap, bytes, sentinel_bytes;
 };
 
@@ -260,6 +311,8 @@ static VoxWorkspace carve(const d3b_voxel_cfg* cfg, int n_total, int batch, char
   w.pslot = (int*)take((size_t)(n_total > 0 ? n_total : 1) * 4);
   w.vslot = (int*)take((size_t)batch * cfg->max_voxels * 4);
   w.cut = (int*)take((size_t)batch * 4);
+  w.chunk_cnt = (int*)take(((size_t)n_total / 1024 + batch + 1) * 4);
+  w.chunk_base = (int*)take(((size_t)n_total / 1024 + batch + 1) * 4);
   w.bytes = off;
   return w;
 }
@@ -297,6 +350,7 @@ extern "C" int d3b_voxelize(const d3b_voxel_cfg* cfg, const float* points,
   for (int b = 0; b <= batch; ++b) {
     p.off[b] = cloud_offsets[b];
     D3B_REQUIRE(b == 0 ? p.off[b] == 0 : p.off[b] >= p.off[b - 1], "d3b_voxelize: cloud_offsets not monotone");
+    p.chunk_off[b] = b == 0 ? 0 : p.chunk_off[b - 1] + (p.off[b] - p.off[b - 1] + kRankChunk - 1) / kRankChunk;
   }
   const int n_total = p.off[batch];
   D3B_REQUIRE(n_total == 0 || points, "d3b_voxelize: null points");
@@ -312,8 +366,17 @@ extern "C" int d3b_voxelize(const d3b_voxel_cfg* cfg, const float* points,
                                                             (unsigned int)(w.cap - 1));
     D3B_LAUNCH_CHECK();
   }
-  vox_rank<<<batch, 1024, 0, stream>>>(p, w.first, w.pslot, w.vid, w.vslot, w.cut, voxel_counts);
+  const int n_chunks = p.chunk_off[batch];
+  if (n_chunks > 0) {
+    vox_chunk_count<<<n_chunks, 256, 0, stream>>>(p, w.first, w.pslot, w.chunk_cnt);
+    D3B_LAUNCH_CHECK();
+  }
+  vox_chunk_scan<<<batch, 1024, 0, stream>>>(p, w.chunk_cnt, w.chunk_base, w.cut, voxel_counts);
   D3B_LAUNCH_CHECK();
+  if (n_chunks > 0) {
+    vox_assign<<<n_chunks, 256, 0, stream>>>(p, w.first, w.pslot, w.chunk_base, w.vid, w.vslot, w.cut);
+    D3B_LAUNCH_CHECK();
+  }
   if (n_total > 0) {
     vox_lists<<<grid_for(n_total, 256), 256, 0, stream>>>(p, w.pslot, w.vid, w.cut, w.lists);
     D3B_LAUNCH_CHECK();
