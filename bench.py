@@ -140,7 +140,7 @@ def run_reference(args, rank, world):
                          "stage_seconds": cpu.timings},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -153,8 +153,26 @@ def workload_config(args, world):
             "cuda_graph": not args.no_graph}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything libraries write to fd 1 (NCCL prints its version there, build tools chat) to stderr, so that
+    stdout carries exactly the one JSON line the contract asks for."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -356,7 +374,7 @@ def main():
                                 "sample": "%d full forwards of one 20k-point cloud through the CPU restatement of the "
                                           "reference path (oracle/second_cpu.py)" % n_cpu,
                                 "stage_seconds": cpu.timings}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
