@@ -98,6 +98,8 @@ SIGNATURES = {
     "d3b_launch_count": (C.c_ulonglong, []),
     "d3b_voxelize_workspace_bytes": (_sz, [C.POINTER(VoxelCfg), _i32, _i32]),
     "d3b_voxelize": (C.c_int, [C.POINTER(VoxelCfg), _vp, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "d3b_ingest_workspace_bytes": (_sz, [_i32]),
+    "d3b_ingest_sweeps": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "d3b_rulebook_workspace_bytes": (_sz, [_i64]),
     "d3b_index_build_hash": (C.c_int, [_vp, _vp, _i32, C.POINTER(SiteIndex), _vp]),
     "d3b_rulebook_subm": (C.c_int, [_vp, _vp, _i32, C.POINTER(SiteIndex), _I3, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -72,6 +72,22 @@ int d3b_voxelize(const d3b_voxel_cfg* cfg, const float* points, const int32_t* c
                  float* mean_feats, int32_t* voxel_counts, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* Multi-sweep ingest (nuScenes): raw sweeps of one sample -> one cloud [n, n_feat + 1] = (x, y, z, .., time lag).
+ * replaces read_file / remove_close / read_sweep and the NuScenes branch of LoadPointCloudFromFile.__call__,
+ * det3d/datasets/pipelines/loading.py:17-64,98-124.
+ * raw            [n_total, raw_stride] f32 device: the sweeps' file contents back to back, key frame first
+ * sweep_offsets  [n_sweeps + 1] i32 HOST, in points
+ * transforms     [n_sweeps, 16] f64 HOST row-major 4x4 (read where has_transform[s]; may be NULL otherwise)
+ * has_transform, filter_close [n_sweeps] u8 HOST, time_lag [n_sweeps] f32 HOST
+ * filter_close[s]: drop points with |x| < radius and |y| < radius before the transform (remove_close)
+ * out            [out_cap, n_feat + 1] f32 device, n_out [1] i32 device = min(kept points, out_cap); input order kept */
+#define D3B_INGEST_MAX_SWEEPS 16
+size_t d3b_ingest_workspace_bytes(int32_t n_points_total);
+int d3b_ingest_sweeps(const float* raw, const int32_t* sweep_offsets, int32_t n_sweeps, int32_t raw_stride,
+                      int32_t n_feat, const double* transforms, const uint8_t* has_transform, const float* time_lag,
+                      const uint8_t* filter_close, float radius, float* out, int32_t out_cap, int32_t* n_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ========================================================================= *
  * 2. Rulebook (sparse-convolution index maps)
  *    replaces spconv v1.x `get_indice_pairs` as called by SubMConv3d /
