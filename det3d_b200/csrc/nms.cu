@@ -483,6 +483,7 @@ pair_matrix_kernel(int na, const float* __restrict__ boxes_a, int nb, const floa
 // real operating point (N = 1000: 2176 CTAs instead of 136).
 constexpr int kNmsRowsPerCta = 16;
 constexpr int kNmsSlices = kNmsBlock / kNmsRowsPerCta;
+constexpr int kNmsPairQueue = 2048;     // queued (row, column) pairs of the iou3d routine; one item adds at most 1024
 
 template <int FMT>  // 0 xyxyr rotated, 1 xywlr rotated, 2 axis-aligned (xyxyr boxes, angle ignored), 3 axis-aligned "+1"
 __global__ void __launch_bounds__(256)
@@ -500,11 +501,25 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
   __shared__ unsigned short s_list[FMT == 1 ? kNmsRowsPerCta * kNmsBlock : 1];
   __shared__ unsigned int s_bits[2 * kNmsRowsPerCta];
   __shared__ int s_count;
+  __shared__ int2 s_pairs[FMT == 0 ? kNmsPairQueue : 1];     // (row box, column box) pairs waiting for the full IoU
+  __shared__ int s_npairs;
+  if (threadIdx.x == 0) s_npairs = 0;
   if (threadIdx.x < 2 * kNmsRowsPerCta) s_bits[threadIdx.x] = 0u;
   if (threadIdx.x == 0) s_count = 0;
   const int tx = threadIdx.x & 63;        // column inside the block
   const int ty = threadIdx.x >> 6;        // 0..3
   unsigned int* mask32 = reinterpret_cast<unsigned int*>(mask);
+  auto flush_pairs = [&]() {              // CTA-uniform: evaluate the queued iou3d pairs, 256 at a time
+    const int n_pairs = s_npairs;
+    for (int e = threadIdx.x; e < n_pairs; e += blockDim.x) {
+      const int2 pr = s_pairs[e];
+      if (iou_xyxyr(boxes + (size_t)pr.x * 5, boxes + (size_t)pr.y * 5) > thresh)
+        atomicOr(&mask32[((size_t)pr.x * col_blocks + (pr.y >> 6)) * 2 + ((pr.y >> 5) & 1)], 1u << (pr.y & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_npairs = 0;
+    __syncthreads();
+  };
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const long long bid = item / kNmsSlices;
     const int slice = (int)(item - bid * kNmsSlices);
@@ -533,6 +548,23 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if (FMT == 1) qrow[r] = quad_of_xywlr(src);
     }
     __syncthreads();
+    if (FMT == 0) {
+      // iou3d pairs: the exact-safe disjoint-circle test rejects > 99 % of the pairs of a large box set; the few
+      // that need the ~2k-instruction polygon routine are queued ACROSS work items and evaluated 256 at a time, so
+      // the expensive part runs with full warps (100k boxes: 205 ms with one or two live lanes per warp).  This CTA
+      // owns the mask words of its items: it zeroes them here and ORs the hits in after the evaluation.
+      if (threadIdx.x < 2 * kNmsRowsPerCta && row_first + (int)(threadIdx.x >> 1) < n)
+        mask32[((size_t)(row_first + (threadIdx.x >> 1)) * col_blocks + col) * 2 + (threadIdx.x & 1)] = 0u;
+      for (int rr = ty; rr < kNmsRowsPerCta; rr += 4) {
+        const int cur = row_first + rr;
+        const bool active = cur < n && tx < col_size && (row != col || tx > slice * kNmsRowsPerCta + rr);
+        if (active && !(thresh >= 0.0f && surely_disjoint(disc_of_xyxyr(srow + rr * 5), dcol[tx])))
+          s_pairs[atomicAdd(&s_npairs, 1)] = make_int2(cur, col * kNmsBlock + tx);
+      }
+      __syncthreads();
+      if (s_npairs > kNmsPairQueue - kNmsRowsPerCta * kNmsBlock) flush_pairs();   // no room for another item
+      continue;
+    }
     if (FMT == 1) {
       // rotate_nms_cc pairs: the hull gate (fp32, a few instructions) passes only a few percent of the pairs, the
       // fp64 polygon clip behind it costs thousands of instructions.  Testing the gate for all 16 x 64 pairs first and
@@ -583,6 +615,10 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if ((threadIdx.x & 31) == 0)
         mask32[((size_t)cur * col_blocks + col) * 2 + ((threadIdx.x >> 5) & 1)] = word;
     }
+  }
+  if (FMT == 0) {
+    __syncthreads();
+    flush_pairs();
   }
 }
 
