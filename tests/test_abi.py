@@ -43,3 +43,31 @@ def test_argument_validation_without_gpu():
     cfg = _lib.VoxelCfg()
     st = L.d3b_voxelize(ctypes.byref(cfg), None, None, 1, None, None, None, None, None, None, 0, None)
     assert st == 1
+
+
+def test_more_argument_validation_without_gpu():
+    """Every entry point validates before it touches CUDA: status 1 (invalid argument) / 3 (unsupported) + message."""
+    L = _lib.lib()
+    i3 = (ctypes.c_int32 * 3)(3, 3, 3)
+    assert L.d3b_rulebook_subm(None, None, 10, None, i3, None, None, None, None, None, None) == 1
+    assert L.d3b_rulebook_pairs(None, None, 10, 27, None, None, None, None) == 1
+    assert L.d3b_zero_rows(None, None, 17, None, 10, None) == 1 and b"count" in L.d3b_last_error()
+    assert L.d3b_zero_rows(None, None, 0, None, 10, None) == 0                 # nothing to do
+    assert L.d3b_rotate_nms(None, 10, None, 7, 0.5, 10, None, (ctypes.c_int32 * 1)(), None, 0, None) == 1
+    assert b"format" in L.d3b_last_error()
+    assert L.d3b_normal_nms(None, 10, None, 5, 0.5, 10, None, (ctypes.c_int32 * 1)(), None, 0, None) == 1
+    assert b"mode" in L.d3b_last_error()
+    one = (ctypes.c_float * 8)()
+    st = L.d3b_pillar_features(one, one, one, one, 4, 100, 2, 64, one, one, one, 0.16, 0.16, 0.0, 0.0, one, None)
+    assert st == 3 and b"ndim" in L.d3b_last_error()                         # D3B_ERR_UNSUPPORTED
+    off = (ctypes.c_int32 * 2)(0, 5)
+    u8 = (ctypes.c_uint8 * 1)(0)
+    lag = (ctypes.c_float * 1)(0.0)
+    n_out = (ctypes.c_int32 * 1)()
+    assert L.d3b_ingest_sweeps(None, off, 40, 5, 4, None, u8, lag, u8, 1.0, None, 5, n_out, None, 0, None) == 1
+    assert b"sweeps" in L.d3b_last_error()
+    assert L.d3b_ingest_sweeps(None, off, 1, 3, 4, None, u8, lag, u8, 1.0, None, 5, n_out, None, 0, None) == 1
+    assert L.d3b_ingest_workspace_bytes(-1) == 0 and L.d3b_nms_workspace_bytes(0) == 16
+    q = _lib.PredictParams()
+    assert L.d3b_predict_workspace_bytes(ctypes.byref(q)) == 0
+    assert L.d3b_predict_task(ctypes.byref(q), None, 0, 0, None, None, 0, None) == 1
