@@ -678,7 +678,18 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
     __syncthreads();
     const unsigned long long kept = kept_word;
     if (kept_total >= max_keep) break;
-    if (kept != 0ULL) {
+    if (kept != 0ULL && stage_mask) {
+      // staged mask (the detector's operating point, nb <= 22): one (kept row, column block) entry per thread instead
+      // of a thread per column block walking up to 64 rows with dependent shared-memory loads
+      const int ncol = nb - (b + 1);
+      for (int e = threadIdx.x; e < kNmsBlock * ncol; e += blockDim.x) {
+        const int i = e / ncol, j = b + 1 + (e - i * ncol);
+        if ((kept >> i) & 1ULL) {
+          const unsigned long long v = smask[(size_t)(b * kNmsBlock + i) * nb + j];
+          if (v != 0ULL) atomicOr(&remv[j], v);
+        }
+      }
+    } else if (kept != 0ULL) {
       for (int j = b + 1 + threadIdx.x; j < nb; j += blockDim.x) {
         unsigned long long acc = remv[j];
         unsigned long long bits = kept;
