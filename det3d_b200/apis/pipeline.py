@@ -56,13 +56,17 @@ class InferencePipeline:
             num_voxels=[None] * batch, shape=[self.grid_size], anchors=self.anchors(batch),
             n_voxels_dev=vox["counts"][batch:batch + 1],
         )
-        prev = torch.backends.cudnn.allow_tf32
+        prev, prev_bench = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
         if self.strict_fp32:
             torch.backends.cudnn.allow_tf32 = False
+        # shapes are static per pipeline: let cuDNN pick its fastest fp32 algorithm for the dense layers that stay on it
+        # (strided / multi-stage RPNs: PointPillars, CBGS)
+        torch.backends.cudnn.benchmark = True
         try:
             det = self.model(example, return_loss=False, device_output=True)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
+            torch.backends.cudnn.benchmark = prev_bench
         det["voxel_counts"] = vox["counts"]
         return det
 
