@@ -153,10 +153,26 @@ topk_finish_kernel(const unsigned long long* __restrict__ part, const int* __res
       for (int j = tid; j < kTopkBins; j += kTopkThreads) hist[j] = 0u;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
-      for (int j = tid; j < n; j += kTopkThreads) {
-        const unsigned long long c = list[j];
-        if (consumed == 0 || (c >> (64 - consumed)) == (prefix >> (64 - consumed)))
-          atomicAdd(&hist[(unsigned int)(c >> shift) & ((1u << bits) - 1u)], 1u);
+      const int n_pad = (n + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
+      for (int j = tid; j < n_pad; j += kTopkThreads) {
+        // this path only runs when the keys are (nearly) all equal in their leading bits, i.e. a warp's digits are
+        // usually identical: one aggregated add per warp then, per-lane adds when they differ
+        bool part = false;
+        unsigned int digit = 0u;
+        if (j < n) {
+          const unsigned long long c = list[j];
+          part = consumed == 0 || (c >> (64 - consumed)) == (prefix >> (64 - consumed));
+          digit = (unsigned int)(c >> shift) & ((1u << bits) - 1u);
+        }
+        const unsigned int pm = __ballot_sync(0xffffffffu, part);
+        if (pm == 0u) continue;
+        const int leader = __ffs(pm) - 1;
+        const unsigned int d0 = __shfl_sync(0xffffffffu, digit, leader);
+        if (__all_sync(0xffffffffu, !part || digit == d0)) {
+          if ((tid & 31) == leader) atomicAdd(&hist[d0], (unsigned int)__popc(pm));
+        } else if (part) {
+          atomicAdd(&hist[digit], 1u);
+        }
       }
       __syncthreads();
       if (tid == 0) {
