@@ -1,5 +1,4 @@
-"""det3d/datasets/registry.py:3-4."""
+"""Dataset-side registries under the reference's names (det3d/datasets/registry.py:3-4)."""
 from det3d_b200.utils.registry import Registry
 
-DATASETS = Registry("dataset")
-PIPELINES = Registry("pipeline")
+DATASETS, PIPELINES = (Registry(kind) for kind in ("dataset", "pipeline"))

@@ -1,11 +1,9 @@
-"""Model registries, same names as det3d/models/registry.py:3-10."""
-from det3d_b200.utils import Registry
+"""The model registries under the reference's names (det3d/models/registry.py:3-10): configs and third-party code
+look components up through `READERS`, `BACKBONES`, `NECKS`, `ROI_EXTRACTORS`, `SHARED_HEADS`, `HEADS`, `LOSSES`,
+`DETECTORS`."""
+from det3d_b200.utils.registry import Registry
 
-READERS = Registry("reader")
-BACKBONES = Registry("backbone")
-NECKS = Registry("neck")
-ROI_EXTRACTORS = Registry("roi_extractor")
-SHARED_HEADS = Registry("shared_head")
-HEADS = Registry("head")
-LOSSES = Registry("loss")
-DETECTORS = Registry("detector")
+_KINDS = ("reader", "backbone", "neck", "roi_extractor", "shared_head", "head", "loss", "detector")
+globals().update({kind.upper() + "S": Registry(kind) for kind in _KINDS})
+LOSSES = globals().pop("LOSSS")          # the one irregular plural
+__all__ = [kind.upper() + "S" for kind in _KINDS if kind != "loss"] + ["LOSSES"]
