@@ -548,7 +548,7 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if (FMT == 1) qrow[r] = quad_of_xywlr(src);
     }
     __syncthreads();
-    if (FMT == 0) {
+    if constexpr (FMT == 0) {
       // iou3d pairs: the exact-safe disjoint-circle test rejects > 99 % of the pairs of a large box set; the few
       // that need the ~2k-instruction polygon routine are queued ACROSS work items and evaluated 256 at a time, so
       // the expensive part runs with full warps (100k boxes: 205 ms with one or two live lanes per warp).  This CTA
@@ -565,7 +565,7 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if (s_npairs > kNmsPairQueue - kNmsRowsPerCta * kNmsBlock) flush_pairs();   // no room for another item
       continue;
     }
-    if (FMT == 1) {
+    if constexpr (FMT == 1) {
       // rotate_nms_cc pairs: the hull gate (fp32, a few instructions) passes only a few percent of the pairs, the
       // fp64 polygon clip behind it costs thousands of instructions.  Testing the gate for all 16 x 64 pairs first and
       // compacting the survivors keeps every lane busy in the expensive part instead of one or two lanes per warp.
@@ -589,6 +589,7 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if (threadIdx.x == 0) s_count = 0;
       continue;                            // the loop-top __syncthreads orders the reset before the next item
     }
+    if constexpr (FMT >= 2) {             // axis-aligned and RRPN routines: cheap enough for the ballot layout
 #pragma unroll 1
     for (int rr = ty; rr < kNmsRowsPerCta; rr += 4) {
       const int cur = row_first + rr;      // warp-uniform
@@ -598,12 +599,7 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       const bool active = tx < col_size && (row != col || tx > slice * kNmsRowsPerCta + rr);
       if (active) {
         const float* cur_box = srow + rr * 5;
-        if (FMT == 0) {
-          const Disc dc = disc_of_xyxyr(cur_box);
-          if (!(thresh >= 0.0f && surely_disjoint(dc, dcol[tx]))) bit = iou_xyxyr(cur_box, scol + tx * 5) > thresh;
-        } else if (FMT == 1) {
-          bit = suppresses_xywlr(qrow[rr], qcol[tx], thresh, nullptr);
-        } else if (FMT == 4) {
+        if (FMT == 4) {
           bit = rrpn_iou(cur_box, scol + tx * 5, -1) > (double)thresh;     // rotate_nms_kernel, nms_gpu.py:411-450
         } else if (FMT == 2) {
           bit = iou_axis_aligned(cur_box, scol + tx * 5) > thresh;
@@ -615,8 +611,9 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
       if ((threadIdx.x & 31) == 0)
         mask32[((size_t)cur * col_blocks + col) * 2 + ((threadIdx.x >> 5) & 1)] = word;
     }
+    }
   }
-  if (FMT == 0) {
+  if constexpr (FMT == 0) {
     __syncthreads();
     flush_pairs();
   }
