@@ -3,6 +3,7 @@
 The library is the product: there is no Python/CPU fallback.  If the shared
 object is missing or a call fails, an exception is raised.
 """
+import contextlib
 import ctypes as C
 import os
 import threading
@@ -163,6 +164,30 @@ def current_stream():
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+@contextlib.contextmanager
+def on_device_of(*tensors):
+    """Scope a group of C-ABI calls to the device that owns `tensors`.
+
+    The kernels launch on `current_stream()`, i.e. on the CURRENT device's stream, so that device must be the one
+    the pointers live on.  All tensors must share one device; when it already is the current one (the usual case:
+    one process per GPU) this costs one integer compare."""
+    import torch
+
+    dev = None
+    for t in tensors:
+        if t is None or not torch.is_tensor(t) or not t.is_cuda:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise D3BError("det3d_b200: tensors of one call live on different devices (%s vs %s)" % (dev, t.device))
+    if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+        yield
+    else:
+        with torch.cuda.device(dev):
+            yield
 
 
 def launch_count():

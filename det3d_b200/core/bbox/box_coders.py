@@ -19,7 +19,11 @@ class GroundBox3dCoderTorch:
         return self.n_dim + 1 if self.vec_encode else self.n_dim
 
     def decode_torch(self, boxes, anchors):
-        return box_torch_ops.second_box_decode(boxes, anchors, self.vec_encode, smooth_dim=self.linear_dim)
+        # Reference quirk, reproduced on purpose (box_coders.py:106-109): `linear_dim` is passed POSITIONALLY and
+        # lands in second_box_decode's ignored `bin_loss` slot (box_torch_ops.py:80-87), and `norm_velo` is never
+        # forwarded -- so the reference always decodes sizes with exp() and velocities without the diagonal,
+        # whatever the coder was built with.  The fused kernel (mg_head.predict_device) follows the same rule.
+        return box_torch_ops.second_box_decode(boxes, anchors, self.vec_encode, self.linear_dim)
 
     def encode_torch(self, boxes, anchors):
         raise NotImplementedError("box encoding is training-only; det3d_b200 covers the inference path")

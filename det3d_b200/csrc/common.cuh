@@ -1,6 +1,8 @@
 // Shared helpers for the det3d_b200 CUDA translation units (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -40,6 +42,26 @@ void count_launch(int n = 1);
       return D3B_ERR_CUDA;                                                          \
     }                                                                               \
   } while (0)
+
+// ---- > 48 KB dynamic shared memory opt-in ----------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: the opt-in is cached per device id
+// (atomics: setting it twice from two threads is benign), never in a process-wide flag.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  std::atomic<int> bytes[kMaxDevices];
+};
+template <typename Kernel>
+static inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, SmemOptIn& cache) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool cached = dev >= 0 && dev < kMaxDevices;
+  if (cached && cache.bytes[dev].load(std::memory_order_acquire) >= (int)bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && cached) cache.bytes[dev].store((int)bytes, std::memory_order_release);
+  return e;
+}
 
 // ---- device constants --------------------------------------------------------
 constexpr int kNumSMs = 148;  // B200

@@ -735,11 +735,8 @@ static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* 
   const size_t staged = smem + (size_t)n_cap * col_blocks * 8;
   const int stage_mask = staged <= 200 * 1024 ? 1 : 0;
   if (stage_mask) smem = staged;
-  static size_t smem_attr = 48 * 1024;
-  if (smem > smem_attr) {
-    D3B_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    smem_attr = 200 * 1024;
-  }
+  static SmemOptIn sweep_optin;
+  if (smem > 48 * 1024) D3B_CUDA(ensure_dynamic_smem(nms_sweep_kernel, 200 * 1024, sweep_optin));
   nms_sweep_kernel<<<1, 1024, smem, stream>>>(mask, n_cap, n_dev, col_blocks, max_keep, keep_idx, keep_count,
                                               stage_mask);
   D3B_LAUNCH_CHECK();

@@ -417,11 +417,8 @@ extern "C" int d3b_predict_task(const d3b_predict_params* q, float* packed, int3
   for (int c = 0; c < 6; ++c) p.range[c] = q->post_center_range[c];
   p.has_range = q->has_range; p.label_offset = q->label_offset;
 
-  static bool finish_attr = false;
-  if (!finish_attr) {
-    D3B_CUDA(cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopkSortCap * 8));
-    finish_attr = true;
-  }
+  static SmemOptIn finish_optin;
+  D3B_CUDA(ensure_dynamic_smem(topk_finish_kernel, (size_t)kTopkSortCap * 8, finish_optin));
   D3B_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)q->batch * (kTopkBins + 1) * 4, stream));
   const dim3 sample_grid((unsigned)std::min(div_up(A, 512), kNumSMs), (unsigned)q->batch);
   head_scores_kernel<<<sample_grid, 256, 0, stream>>>(q->cls, q->cls_row_stride, q->cls_col0, q->hw, q->na, q->n_cls,

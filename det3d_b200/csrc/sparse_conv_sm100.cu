@@ -776,11 +776,8 @@ template <int COUT>
 static int launch_tc(const float* feat_in, const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out,
                      int32_t out_cap, const d3b_conv_params* p, float* feat_out, cudaStream_t stream) {
   using Cfg = TcCfg<COUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    D3B_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  D3B_CUDA(ensure_dynamic_smem(spconv_tc_kernel<COUT>, Cfg::kSmemBytes, optin));
   const int n_tiles = div_up(out_cap, kTcTileM);
   const int grid = n_tiles < kNumSMs ? (n_tiles > 0 ? n_tiles : 1) : kNumSMs;
   const int n_kb = (p->c_in + kTcKc - 1) / kTcKc;
@@ -795,11 +792,8 @@ template <int COUT>
 static int launch_pairs(const float* feat_in, const int32_t* n_out, int32_t out_cap, const d3b_conv_params* p,
                         float* feat_out, cudaStream_t stream) {
   using Cfg = TcCfg<COUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    D3B_CUDA(cudaFuncSetAttribute(spconv_pairs_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem<COUT>));
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  D3B_CUDA(ensure_dynamic_smem(spconv_pairs_kernel<COUT>, kPairSmem<COUT>, optin));
   if (!p->out_zeroed) {
     zero_rows_kernel<<<grid_for((long long)out_cap * COUT / 4, 256), 256, 0, stream>>>(feat_out, n_out, out_cap, COUT);
     D3B_LAUNCH_CHECK();

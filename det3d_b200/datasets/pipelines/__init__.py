@@ -1,1 +1,4 @@
-from .loading import LoadPointCloudFromFile, ingest_sweeps, read_file
+from .compose import Compose
+from .formating import Reformat
+from .loading import LoadPointCloudAnnotations, LoadPointCloudFromFile, ingest_sweeps, read_file
+from .preprocess import AssignTarget, Preprocess, Voxelization

@@ -115,3 +115,50 @@ class LoadPointCloudFromFile(object):
         else:
             raise NotImplementedError("LoadPointCloudFromFile: dataset type %s" % self.type)
         return res, info
+
+
+def _kitti_boxes_camera_to_lidar(annos, r_rect, velo2cam):
+    """location/dimensions/rotation_y (camera frame, bottom-centre) -> lidar boxes [n,7] x,y,z,w,l,h,r with the
+    gravity centre: box_np_ops.box_camera_to_lidar + change_box3d_center_ (box_np_ops.py:909-930,1346-1349)."""
+    gt = np.concatenate([annos["location"], annos["dimensions"], annos["rotation_y"][..., np.newaxis]], axis=1).astype(np.float32)
+    xyz = np.concatenate([gt[:, 0:3], np.ones((gt.shape[0], 1))], axis=-1)
+    xyz_lidar = (xyz @ np.linalg.inv((r_rect @ velo2cam).T))[..., :3]
+    l, h, w, r = gt[:, 3:4], gt[:, 4:5], gt[:, 5:6], gt[:, 6:7]
+    boxes = np.concatenate([xyz_lidar, w, l, h, r], axis=1)
+    boxes[..., :3] += boxes[..., 3:6] * (np.array([0.5, 0.5, 0.5], boxes.dtype) - np.array([0.5, 0.5, 0], boxes.dtype))
+    return boxes
+
+
+@PIPELINES.register_module
+class LoadPointCloudAnnotations(object):
+    """det3d/datasets/pipelines/loading.py:165-224: calibration + (when the info record has them) ground-truth boxes
+    for evaluation.  Host metadata only -- nothing here is on the compute path."""
+
+    def __init__(self, with_bbox=True, **kwargs):
+        pass
+
+    def __call__(self, res, info):
+        if res["type"] in ["NuScenesDataset", "LyftDataset"] and "gt_boxes" in info:
+            res["lidar"]["annotations"] = {
+                "boxes": info["gt_boxes"].astype(np.float32),
+                "names": info["gt_names"],
+                "tokens": info["gt_boxes_token"],
+                "velocities": info["gt_boxes_velocity"].astype(np.float32),
+            }
+        elif res["type"] == "KittiDataset":
+            calib = info["calib"]
+            res["calib"] = {"rect": calib["R0_rect"], "Trv2c": calib["Tr_velo_to_cam"], "P2": calib["P2"]}
+            if "annos" in info:
+                annos = info["annos"]
+                keep = [i for i, x in enumerate(annos["name"]) if x != "DontCare"]       # kitti_common.remove_dontcare
+                annos = {k: v[keep] for k, v in annos.items()}
+                res["lidar"]["annotations"] = {
+                    "boxes": _kitti_boxes_camera_to_lidar(annos, calib["R0_rect"], calib["Tr_velo_to_cam"]),
+                    "names": annos["name"],
+                }
+                res.setdefault("cam", {})["annotations"] = {"boxes": annos["bbox"], "names": annos["name"]}
+        elif res["type"] in ["NuScenesDataset", "LyftDataset"]:
+            pass
+        else:
+            raise NotImplementedError("LoadPointCloudAnnotations: dataset type %r" % (res["type"],))
+        return res, info

@@ -179,6 +179,23 @@ class MultiGroupHead(nn.Module):
             valid = valid & (boxes[..., :3] >= r[:3]).all(-1) & (boxes[..., :3] <= r[3:]).all(-1)
         return boxes, scores, labels, valid
 
+    def _check_supported(self, example, **kwargs):
+        """Inputs the reference's predict treats specially and this path does not implement: fail, never differ."""
+        if isinstance(example, dict) and example.get("anchors_mask") is not None:
+            raise NotImplementedError("example['anchors_mask'] (pos_area_threshold >= 0, mg_head.py:760-767,983-993) is "
+                                      "not implemented on the device predict path")
+        if kwargs.get("mode") is not None:
+            raise NotImplementedError("predict(mode=...) (bev_only path) is not implemented")
+        seen = self.__dict__.setdefault("_anchor_batch_checked", set())
+        for a in example["anchors"]:
+            if a.dim() >= 3 and a.shape[0] > 1 and a.stride(0) != 0:
+                key = (a.data_ptr(), a._version, tuple(a.shape))
+                if key not in seen:      # one-time check per anchor tensor (synchronises once)
+                    if not bool((a == a[:1]).all()):
+                        raise NotImplementedError("per-sample anchors differ: the device predict path assumes one "
+                                                  "anchor set per task shared by the batch")
+                    seen.add(key)
+
     @staticmethod
     def _rows(t, batch):
         """[B,H,W,n] head tensor (contiguous or a column slice of fused rows) -> (ptr, row stride in floats, hw)."""
@@ -195,6 +212,7 @@ class MultiGroupHead(nn.Module):
         D = sum over tasks of nms_post_max_size; labels already offset per task.  One d3b_predict_task
         call (five kernels + NMS) per task; `use_torch_ops=True` runs the same algorithm with torch
         ops (kept as an in-repo cross-check of the fused kernels)."""
+        self._check_supported(example)
         if use_torch_ops:
             return self._predict_device_torch(example, preds_dicts, test_cfg)
         import ctypes as C
@@ -237,8 +255,9 @@ class MultiGroupHead(nn.Module):
             q.code = self.box_n_dim - 2 if self.bev_only else self.box_n_dim
             q.nd = nd
             q.vec_encode = 1 if self.box_coder.vec_encode else 0
-            q.smooth_dim = 1 if self.box_coder.linear_dim else 0
-            q.norm_velo = 1 if getattr(self.box_coder, "norm_velo", False) else 0
+            # the reference's decode_torch never reaches smooth_dim / norm_velo (see box_coders.decode_torch)
+            q.smooth_dim = 0
+            q.norm_velo = 0
             q.use_rotate_nms = 1 if nms_cfg["use_rotate_nms"] else 0
             q.pre_max, q.post_max = pre, post
             q.nms_iou_threshold = float(nms_cfg["nms_iou_threshold"])
@@ -252,8 +271,9 @@ class MultiGroupHead(nn.Module):
             ws = bufs["ws"].get(task_id)
             if ws is None or ws.numel() < need:
                 ws = bufs["ws"][task_id] = torch.empty(need, dtype=torch.uint8, device=dev)
-            st = _lib.lib().d3b_predict_task(C.byref(q), packed.data_ptr(), D, row_offset, None, ws.data_ptr(),
-                                            ws.numel(), _lib.current_stream())
+            with _lib.on_device_of(packed, first):
+                st = _lib.lib().d3b_predict_task(C.byref(q), packed.data_ptr(), D, row_offset, None, ws.data_ptr(),
+                                                ws.numel(), _lib.current_stream())
             _lib.check(st, "d3b_predict_task")
             row_offset += post
             flag += n_cls
@@ -280,6 +300,7 @@ class MultiGroupHead(nn.Module):
 
     def predict(self, example, preds_dicts, test_cfg, **kwargs):
         """list (per sample) of dict(box3d_lidar [K,nd], scores [K], label_preds [K], metadata)."""
+        self._check_supported(example, **kwargs)
         det = self.predict_device(example, preds_dicts, test_cfg)
         B = det["boxes"].shape[0]
         meta = example.get("metadata") if isinstance(example, dict) else None

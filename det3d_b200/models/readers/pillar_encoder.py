@@ -90,11 +90,12 @@ class PillarFeatureNet(nn.Module):
         out = torch.empty((m, layer.units), dtype=torch.float32, device=features.device)
         if n_dev is None:
             n_dev = torch.tensor([m], dtype=torch.int32, device=features.device)
-        st = _lib.lib().d3b_pillar_features(
-            features.contiguous().data_ptr(), num_voxels.to(torch.int32).contiguous().data_ptr(),
-            coors.to(torch.int32).contiguous().data_ptr(), n_dev.data_ptr(), m, p, ndim, layer.units, w.data_ptr(),
-            scale.data_ptr(), shift.data_ptr(), C.c_float(self.vx), C.c_float(self.vy), C.c_float(self.x_offset),
-            C.c_float(self.y_offset), out.data_ptr(), _lib.current_stream())
+        with _lib.on_device_of(features, num_voxels, coors, n_dev):
+            st = _lib.lib().d3b_pillar_features(
+                features.contiguous().data_ptr(), num_voxels.to(torch.int32).contiguous().data_ptr(),
+                coors.to(torch.int32).contiguous().data_ptr(), n_dev.data_ptr(), m, p, ndim, layer.units, w.data_ptr(),
+                scale.data_ptr(), shift.data_ptr(), C.c_float(self.vx), C.c_float(self.vy), C.c_float(self.x_offset),
+                C.c_float(self.y_offset), out.data_ptr(), _lib.current_stream())
         _lib.check(st, "d3b_pillar_features")
         return out[:m]
 

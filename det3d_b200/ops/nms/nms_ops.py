@@ -32,14 +32,15 @@ def nms_sorted(boxes_sorted, fmt, thresh, max_keep=None, n_dev=None, axis_aligne
         keep_idx, keep_count = out
     ws = _workspace(n, dev)
     L = _lib.lib()
-    if axis_aligned:
-        st = L.d3b_normal_nms(boxes_sorted.data_ptr(), n, _lib.ptr(n_dev), int(aa_mode), float(thresh), max_keep,
-                              keep_idx.data_ptr(), keep_count.data_ptr(), ws.data_ptr(), ws.numel(),
-                              _lib.current_stream())
-    else:
-        st = L.d3b_rotate_nms(boxes_sorted.data_ptr(), n, _lib.ptr(n_dev), int(fmt), float(thresh), max_keep,
-                              keep_idx.data_ptr(), keep_count.data_ptr(), ws.data_ptr(), ws.numel(),
-                              _lib.current_stream())
+    with _lib.on_device_of(boxes_sorted, n_dev, keep_idx, keep_count):
+        if axis_aligned:
+            st = L.d3b_normal_nms(boxes_sorted.data_ptr(), n, _lib.ptr(n_dev), int(aa_mode), float(thresh), max_keep,
+                                  keep_idx.data_ptr(), keep_count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _lib.current_stream())
+        else:
+            st = L.d3b_rotate_nms(boxes_sorted.data_ptr(), n, _lib.ptr(n_dev), int(fmt), float(thresh), max_keep,
+                                  keep_idx.data_ptr(), keep_count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _lib.current_stream())
     _lib.check(st, "d3b nms")
     return keep_idx, keep_count
 
@@ -71,7 +72,8 @@ def boxes_iou_bev(boxes_a, boxes_b, mode=0):
     a = boxes_a.float().contiguous()
     b = boxes_b.float().contiguous()
     out = torch.zeros((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
-    st = _lib.lib().d3b_boxes_iou_bev(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], int(mode),
-                                      out.data_ptr(), _lib.current_stream())
+    with _lib.on_device_of(a, b):
+        st = _lib.lib().d3b_boxes_iou_bev(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], int(mode),
+                                          out.data_ptr(), _lib.current_stream())
     _lib.check(st, "d3b_boxes_iou_bev")
     return out

@@ -82,10 +82,11 @@ class Voxelizer:
         batch = len(offsets) - 1
         b = self._buffers(n_total, batch, ndim, points.device)
         off = (C.c_int32 * (batch + 1))(*[int(o) for o in offsets])
-        st = _lib.lib().d3b_voxelize(
-            C.byref(b["cfg"]), points.data_ptr() if n_total > 0 else None, off, batch,
-            _lib.ptr(b["voxels"]), b["coors"].data_ptr(), b["num_points"].data_ptr(), _lib.ptr(b["mean"]),
-            b["counts"].data_ptr(), b["ws"].data_ptr(), b["ws"].numel(), _lib.current_stream(),
-        )
+        with _lib.on_device_of(points):
+            st = _lib.lib().d3b_voxelize(
+                C.byref(b["cfg"]), points.data_ptr() if n_total > 0 else None, off, batch,
+                _lib.ptr(b["voxels"]), b["coors"].data_ptr(), b["num_points"].data_ptr(), _lib.ptr(b["mean"]),
+                b["counts"].data_ptr(), b["ws"].data_ptr(), b["ws"].numel(), _lib.current_stream(),
+            )
         _lib.check(st, "d3b_voxelize")
         return {k: b[k] for k in ("voxels", "coors", "num_points", "mean", "counts")}

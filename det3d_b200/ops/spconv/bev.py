@@ -153,6 +153,10 @@ class FusedBevStack:
         return t
 
     def run(self, rows, batch, height, width):
+        with _lib.on_device_of(rows):
+            return self._run(rows, batch, height, width)
+
+    def _run(self, rows, batch, height, width):
         """rows [B*H*W, C] channels-last BEV features -> list (per task) of dicts like Head.forward:
         box_preds [B,H,W,a*code], cls_preds [B,H,W,a*cls], dir_cls_preds [B,H,W,a*2]."""
         device = rows.device

@@ -156,6 +156,10 @@ class FusedSparseEncoder:
 
     # ---- run ------------------------------------------------------------------------
     def run(self, features, coors, batch_size, spatial, n_dev=None, row_cap=None, bev_rows=False):
+        with _lib.on_device_of(features, coors, n_dev):
+            return self._run(features, coors, batch_size, spatial, n_dev, row_cap, bev_rows)
+
+    def _run(self, features, coors, batch_size, spatial, n_dev=None, row_cap=None, bev_rows=False):
         """features [M, C] f32, coors [M, 4] int (b,z,y,x) -> dense [B, C_out, D, H, W].
 
         With `n_dev` (int32[>=1] device tensor) only the first n_dev[0] rows are
