@@ -73,6 +73,29 @@ class ConvParams(C.Structure):
     ]
 
 
+class Conv16Params(C.Structure):
+    _fields_ = [
+        ("c_in", C.c_int32), ("c_out", C.c_int32), ("k_vol", C.c_int32),
+        ("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("in_f32", C.c_void_p),
+        ("weight", C.c_void_p), ("weight_packed", C.c_void_p), ("acc_scale", C.c_float),
+        ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("residual_hi", C.c_void_p), ("residual_lo", C.c_void_p), ("relu", C.c_int32),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p), ("overflow", C.c_void_p),
+    ]
+
+
+class Bev16Params(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32), ("c_in", C.c_int32),
+        ("c_out", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("groups", C.c_int32), ("cgroups", C.c_int32), ("up", C.c_int32),
+        ("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("weight_packed", C.c_void_p), ("acc_scale", C.c_float),
+        ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int32),
+        ("out_channels", C.c_int32), ("out_c0", C.c_int32),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p), ("overflow", C.c_void_p),
+    ]
+
+
 class PredictParams(C.Structure):
     _fields_ = [
         ("cls", C.c_void_p), ("cls_row_stride", C.c_int32), ("cls_col0", C.c_int32),
@@ -115,6 +138,13 @@ SIGNATURES = {
     "d3b_pillar_features": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "d3b_sparse_to_bev_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_rulebook_dense2d": (C.c_int, [_i32, _i32, _i32, C.c_int32 * 2, C.c_int32 * 2, _vp, _vp, _vp, _vp]),
+    "d3b_conv16_packed_weight_halves": (_sz, [_i32, _i32, _i32]),
+    "d3b_conv16_pack_weight": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "d3b_sparse_conv16": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(Conv16Params), _vp]),
+    "d3b_split16": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "d3b_merge16": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "d3b_sparse_to_bev16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp, _vp]),
+    "d3b_bev_conv16": (C.c_int, [C.POINTER(Bev16Params), _vp]),
     "d3b_predict_workspace_bytes": (_sz, [C.POINTER(PredictParams)]),
     "d3b_predict_task": (C.c_int, [C.POINTER(PredictParams), _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "d3b_boxes_iou_bev": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),

@@ -10,6 +10,9 @@ with fixed-shape buffers: points are voxelized for the whole batch in one call w
 batch index and the VoxelFeatureExtractorV3 mean fused in, anchors are generated once
 and cached on the device, and detections come back as fixed-shape tensors.
 """
+import collections
+import warnings
+
 import numpy as np
 import torch
 
@@ -38,7 +41,9 @@ class InferencePipeline:
         self._anchors = [torch.from_numpy(a).to(self.device) for a in anchors]
         self._anchor_cache = {}
         self.strict_fp32 = strict_fp32
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()      # offsets tuple -> captured graph, least recently used first
+        self.max_graphs = 8
+        self._ovf_host = None
 
     def anchors(self, batch):
         a = self._anchor_cache.get(batch)
@@ -70,6 +75,23 @@ class InferencePipeline:
         det["voxel_counts"] = vox["counts"]
         return det
 
+    # ---- f16-range guard of the FP16x3 kernels -------------------------------------------------------------------
+    def overflow_flag(self):
+        """Device int32[1]: nonzero once a feature left the f16 range (the FP16x3 kernels never saturate silently)."""
+        flag = getattr(self.model, "overflow_flag", None)
+        return None if flag is None else flag(self.device)
+
+    def check_overflow(self, flag_value):
+        """Host side of the guard: on a raised flag switch the model to the tf32x3 kernels (permanently: the weights /
+        inputs that overflowed once will again) and tell the caller to re-run.  Returns True if a re-run is needed."""
+        if not flag_value:
+            return False
+        warnings.warn("det3d_b200: a feature left the f16 range (|x| >= 65504); re-running on the tf32x3 kernels")
+        self.model.set_math("tf32x3")
+        self.overflow_flag().zero_()
+        self._graphs.clear()
+        return True
+
     @torch.no_grad()
     def forward_graphed(self, points, offsets):
         """forward_device + pack replayed from a CUDA graph (captured on first use per `offsets`).
@@ -80,7 +102,14 @@ class InferencePipeline:
         Returns the packed detections [B, D, nd+3] (a static buffer: consume before the next call)."""
         key = tuple(int(o) for o in offsets)
         entry = self._graphs.get(key)
+        if entry is not None:
+            self._graphs.move_to_end(key)
         if entry is None:
+            # One graph per distinct `offsets` (the per-cloud point counts are host arguments of d3b_voxelize).  Real
+            # LiDAR frames rarely repeat a point count: keep at most `max_graphs` graphs (LRU) so memory stays bounded;
+            # callers with free-running sizes should pad clouds to a few bucket sizes or use forward_device.
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.popitem(last=False)
             static_pts = torch.zeros((key[-1], points.shape[1]), dtype=torch.float32, device=self.device)
             static_pts.copy_(points)
             side = torch.cuda.Stream(device=self.device)
@@ -118,11 +147,19 @@ class InferencePipeline:
         pts = torch.empty((offsets[-1], ndim), dtype=torch.float32, device=self.device)
         for c, a, b in zip(clouds, offsets[:-1], offsets[1:]):
             pts[a:b].copy_(c, non_blocking=True)
-        packed = self.pack(self.forward_device(pts, offsets))
-        if pinned_out is None:
-            pinned_out = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
-        pinned_out.copy_(packed, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        for _attempt in range(2):
+            packed = self.pack(self.forward_device(pts, offsets))
+            if pinned_out is None:
+                pinned_out = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+            pinned_out.copy_(packed, non_blocking=True)
+            flag = self.overflow_flag()
+            if flag is not None:
+                if self._ovf_host is None:
+                    self._ovf_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+                self._ovf_host.copy_(flag, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if flag is None or not self.check_overflow(int(self._ovf_host[0])):
+                break
         return pinned_out
 
     @staticmethod

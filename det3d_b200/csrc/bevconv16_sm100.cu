@@ -1,0 +1,420 @@
+// Dense BEV convolutions (RPN blocks, deblocks, task heads) as implicit GEMMs on tcgen05, sm_100a.
+//
+// Reference: det3d/models/necks/rpn.py:82-159 (ZeroPad2d + Conv2d 3x3 [stride s] + BN + ReLU, n x (Conv2d 3x3 + BN +
+// ReLU), deblock = Conv2d 1x1 / ConvTranspose2d(k = s, stride = s) + BN + ReLU, channel concat) and the 1x1 heads of
+// det3d/models/bbox_heads/mg_head.py:198-230 -- fp32 cuDNN there.
+//
+// Round 1 ran these layers through the sparse gather kernel with a static "dense" rulebook: a dense tensor was
+// re-gathered nine times through registers and st.shared, and the M128 x N128 SS-MMAs re-read both operands for each
+// of the three split products -- the shared-memory pipe was the limiter (ncu: L1/shared 96 %, tensor 52 %).  Here:
+//
+//  * Activations are NHWC f16 planes (hi = f16(x), lo = f16(x - hi), see spconv16_sm100.cu), loaded by TMA with a 4-D
+//    tensor map (C, W, H, B): box = 64 channels x 8 pixels x (16 + K - 1) rows, 128-byte swizzle, out-of-bounds
+//    coordinates (the conv's zero padding, image borders, other samples) zero-filled by the TMA unit.  No thread
+//    touches an activation on its way to the tensor core.
+//  * Tile = 16 x 16 output pixels x C_out: two M = 128 halves (16 rows x 8 columns each) that share every weight
+//    stage.  In a patch, eight consecutive 128-byte rows are one image row segment, so the matrix for kernel row ky is
+//    the SAME staged patch with the UMMA descriptor start advanced by ky * 1024 bytes: one patch load per (kx, 64
+//    channels) serves three (ky, kx) offsets.
+//  * FP16x3: per k-step two MMAs, A_hi x [B_hi | B_lo] (N = 2 C_out) and A_lo x B_hi (N = C_out), fp32 accumulation
+//    in TMEM (all 512 columns at C_out = 128); the epilogue adds the two column halves and applies bias / BN / ReLU.
+//  * Warp roles: 1 TMA warp, 1 MMA warp, 8 epilogue warps (one per TMEM quadrant and half); A ring of 2 stages
+//    (4 patches each), B ring of 2..4 stages, all mbarrier-driven; persistent grid (143 tiles at 200 x 176).
+//  * stride 2 (RPN down-sampling blocks): the box is loaded with elementStrides = 2, one load per (ky, kx).
+//  * groups: several weight blocks over the same input in one launch -- C_out = 256 as two N = 128 passes, and
+//    ConvTranspose2d(k = s, stride = s) as s*s 1x1 convolutions whose epilogues write pixel (y*s + dy, x*s + dx)
+//    into a channel slice of the concat buffer.
+//
+// Bound: tensor pipe (kind::f16).  fp32-equivalent flops per launch = 2 * B*H*W * K*K * C_in * C_out; the pipe
+// executes 3x that.  Algorithmic bytes = B*H*W*(C_in + C_out)*4 + K*K*C_in*C_out*4.
+#include <cuda.h>
+
+#include "umma.cuh"
+
+namespace d3b {
+
+struct BvEpi {          // same fields as spconv16_sm100.cu (kept local: the two kernels are separate TUs)
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  float acc_scale;
+  int relu;
+};
+
+constexpr int kBvTileY = 16, kBvTileX = 16;     // output pixels per tile
+constexpr int kBvHalfX = 8;                     // one M = 128 half = 16 rows x 8 columns
+constexpr int kBvKc = 64;                       // channels per stage (128 bytes of f16)
+constexpr int kBvTmaWarp = 0, kBvMmaWarp = 1, kBvEpiWarp0 = 2;
+constexpr int kBvThreads = 32 * (kBvEpiWarp0 + 8);   // 320
+constexpr int kBvAStages = 2;
+
+template <int KS, int STRIDE, int COUT>
+struct BvCfg {
+  static constexpr int kPatchRows = STRIDE == 1 ? kBvTileY + KS - 1 : kBvTileY;      // rows in one staged patch
+  static constexpr int kPatchBytes = kPatchRows * kBvHalfX * 128;
+  static constexpr int kAStageBytes = 4 * kPatchBytes;                                // {half 0, half 1} x {hi, lo}
+  static constexpr int kBBytes = 2 * COUT * 128;                                      // [B_hi rows | B_lo rows]
+  static constexpr int kBStages = COUT >= 128 ? 2 : 4;
+  static constexpr int kAccCols = 2 * COUT;                                           // per half
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;             // both halves
+  static constexpr int kSmemBytes = kBvAStages * kAStageBytes + kBStages * kBBytes + 1024 + 256;
+  // with stride 1 one A stage serves the KS kernel rows of a (kx, kb); with stride 2 every (ky, kx) has its own
+  static constexpr int kRowsPerAStage = STRIDE == 1 ? KS : 1;
+};
+
+struct BvGeom {
+  int batch, h_out, w_out;        // conv output grid
+  int c_in, n_kb;
+  int pad;
+  int tiles_y, tiles_x;           // per sample
+  int groups, cgroups;            // weight blocks; cgroups of them tile the output channels, the rest are (uy, ux)
+  int up;                         // output pixel = (y*up + uy, x*up + ux)
+  int out_h, out_w;               // output tensor grid (h_out*up, w_out*up)
+  int out_channels, out_c0;       // row length of the output tensor and first channel written
+};
+
+__device__ __forceinline__ uint32_t bv_pack_half2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+template <int KS, int STRIDE, int COUT>
+__global__ void __launch_bounds__(kBvThreads, 1)
+bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, BvGeom g,
+                  const __half* __restrict__ packed, BvEpi epi, __half* __restrict__ out_hi,
+                  __half* __restrict__ out_lo, float* __restrict__ out_f32, int* __restrict__ overflow) {
+  using Cfg = BvCfg<KS, STRIDE, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + kBvAStages * Cfg::kAStageBytes;
+  const uint32_t bar_base = b_base + Cfg::kBStages * Cfg::kBBytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kBvAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kBvAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kBvAStages + Cfg::kBStages + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages);
+  const uint32_t acc_empty = acc_full + 8u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kBvAStages + 2 * Cfg::kBStages + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_group = g.batch * g.tiles_y * g.tiles_x;
+  const int n_tiles = tiles_per_group * g.groups;
+  const int k_vol = KS * KS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBvAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 256);         // the eight epilogue warps
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+  }
+  if (warp == kBvMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  // tile -> (group, sample, y0, x0)
+  auto decode = [&](int tile, int& grp, int& b, int& y0, int& x0) {
+    grp = tile / tiles_per_group;
+    int t = tile - grp * tiles_per_group;
+    b = t / (g.tiles_y * g.tiles_x);
+    t -= b * g.tiles_y * g.tiles_x;
+    y0 = (t / g.tiles_x) * kBvTileY;
+    x0 = (t % g.tiles_x) * kBvTileX;
+  };
+
+  if (warp == kBvTmaWarp) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int grp, b, y0, x0;
+        decode(tile, grp, b, y0, x0);
+        const __half* wgrp = packed + (size_t)grp * k_vol * g.n_kb * (Cfg::kBBytes / 2);
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          for (int kx = 0; kx < KS; ++kx) {
+            for (int ky0 = 0; ky0 < KS; ky0 += Cfg::kRowsPerAStage) {
+              // ---- A stage: {half 0, half 1} x {hi, lo} patches ----
+              const int sa = a_it % kBvAStages;
+              mbar_wait(a_empty(sa), ((a_it / kBvAStages) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(a_full(sa), Cfg::kAStageBytes);
+              const uint32_t dst = a_base + sa * Cfg::kAStageBytes;
+              const int cy = STRIDE == 1 ? y0 - g.pad : y0 * STRIDE + ky0 - g.pad;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int cx = (x0 + half * kBvHalfX) * STRIDE + kx - g.pad;
+                tma_load_4d(dst + (2 * half) * Cfg::kPatchBytes, &tm_hi, kb * kBvKc, cx, cy, b, a_full(sa));
+                tma_load_4d(dst + (2 * half + 1) * Cfg::kPatchBytes, &tm_lo, kb * kBvKc, cx, cy, b, a_full(sa));
+              }
+              ++a_it;
+              // ---- B stages: one per kernel row served by this A stage ----
+              for (int r = 0; r < Cfg::kRowsPerAStage; ++r) {
+                const int ky = ky0 + r;
+                const int sb = b_it % Cfg::kBStages;
+                mbar_wait(b_empty(sb), ((b_it / Cfg::kBStages) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(b_full(sb), Cfg::kBBytes);
+                tma_bulk_g2s(b_base + sb * Cfg::kBBytes,
+                             wgrp + ((size_t)(ky * KS + kx) * g.n_kb + kb) * (Cfg::kBBytes / 2), Cfg::kBBytes, b_full(sb));
+                ++b_it;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kBvMmaWarp) {
+    // ===================== MMA issuer (one elected lane) =====================
+    constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * COUT);   // A_hi x [B_hi | B_lo]
+    constexpr uint32_t idesc1 = umma_idesc_f16(128, COUT);       // A_lo x B_hi
+    uint32_t a_it = 0, b_it = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      mbar_wait(acc_empty, (tile_it & 1u) ^ 1u);
+      tc_fence_after();
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < g.n_kb; ++kb) {
+        const int n_ks = min(kBvKc / 16, (g.c_in - kb * kBvKc + 15) / 16);
+        for (int kx = 0; kx < KS; ++kx) {
+          for (int ky0 = 0; ky0 < KS; ky0 += Cfg::kRowsPerAStage) {
+            const int sa = a_it % kBvAStages;
+            mbar_wait(a_full(sa), (a_it / kBvAStages) & 1u);
+            for (int r = 0; r < Cfg::kRowsPerAStage; ++r, ++b_it) {
+              const int sb = b_it % Cfg::kBStages;
+              mbar_wait(b_full(sb), (b_it / Cfg::kBStages) & 1u);
+              tc_fence_after();
+              if (lane == 0) {
+                const uint32_t bt = b_base + sb * Cfg::kBBytes;
+                // stride 1: kernel row r of the staged patch = the same bytes 8 rows (1024 B) further down
+                const uint32_t row_adv = STRIDE == 1 ? (uint32_t)(ky0 + r) * 1024u : 0u;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const uint32_t ah = a_base + sa * Cfg::kAStageBytes + (2 * half) * Cfg::kPatchBytes + row_adv;
+                  const uint32_t al = ah + Cfg::kPatchBytes;
+                  const uint32_t d_addr = tmem_d + half * Cfg::kAccCols;
+                  for (int ks = 0; ks < n_ks; ++ks) {
+                    const uint32_t adv = ks * 32;
+                    tc_mma_f16(d_addr, umma_desc_sw128(ah + adv), umma_desc_sw128(bt + adv), idesc2, accumulate | (uint32_t)(ks > 0));
+                    tc_mma_f16(d_addr, umma_desc_sw128(al + adv), umma_desc_sw128(bt + adv), idesc1, 1u);
+                  }
+                }
+                tc_commit(b_empty(sb));
+              }
+              __syncwarp();
+              accumulate = 1u;
+            }
+            if (lane == 0) tc_commit(a_empty(sa));
+            __syncwarp();
+            ++a_it;
+          }
+        }
+      }
+      if (lane == 0) tc_commit(acc_full);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: TMEM -> bias / BN / ReLU -> NHWC planes =====================
+    const int ew = warp - kBvEpiWarp0;          // 0..7
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;
+    const int m = quad * 32 + lane;             // pixel of the half: row m / 8, column m % 8
+    bool ovf = false;
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      int grp, b, y0, x0;
+      decode(tile, grp, b, y0, x0);
+      const int y = y0 + (m >> 3), x = x0 + half * kBvHalfX + (m & 7);
+      const bool live = y < g.h_out && x < g.w_out;
+      const int cg = grp % g.cgroups, ug = grp / g.cgroups;
+      const int oy = y * g.up + ug / g.up, ox = x * g.up + ug % g.up;
+      const size_t row_off = (((size_t)b * g.out_h + oy) * g.out_w + ox) * (size_t)g.out_channels + g.out_c0 + cg * COUT;
+      const int pcol = grp * COUT;              // per-group epilogue parameters are laid out group-major
+      mbar_wait(acc_full, tile_it & 1u);
+      tc_fence_after();
+      const uint32_t t0 = tmem_d + half * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t r1[16], r2[16];
+        tc_ld16_nowait(t0 + c0, r1);
+        tc_ld16_nowait(t0 + COUT + c0, r2);
+        tc_ld_wait();
+        if (!live) continue;
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = (__uint_as_float(r1[q]) + __uint_as_float(r2[q])) * epi.acc_scale;
+        if (epi.bias) {
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(epi.bias + pcol + c0 + q));
+            v[q] += bb.x; v[q + 1] += bb.y; v[q + 2] += bb.z; v[q + 3] += bb.w;
+          }
+        }
+        if (epi.scale) {
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(epi.scale + pcol + c0 + q));
+            const float4 t = __ldg(reinterpret_cast<const float4*>(epi.shift + pcol + c0 + q));
+            v[q] = fmaf(v[q], s.x, t.x); v[q + 1] = fmaf(v[q + 1], s.y, t.y);
+            v[q + 2] = fmaf(v[q + 2], s.z, t.z); v[q + 3] = fmaf(v[q + 3], s.w, t.w);
+          }
+        }
+        if (epi.relu) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (out_hi) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 16; q += 2) {
+            __half h0, l0, h1, l1;
+            split_f16(v[q], h0, l0);
+            split_f16(v[q + 1], h1, l1);
+            hi[q >> 1] = bv_pack_half2(h0, h1);
+            lo[q >> 1] = bv_pack_half2(l0, l1);
+            ovf |= !(fabsf(v[q]) < 65504.f) | !(fabsf(v[q + 1]) < 65504.f);
+          }
+          uint4* ph = reinterpret_cast<uint4*>(out_hi + row_off + c0);
+          uint4* pl = reinterpret_cast<uint4*>(out_lo + row_off + c0);
+          ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+        if (out_f32) {
+          float4* pf = reinterpret_cast<float4*>(out_f32 + row_off + c0);
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) pf[q >> 2] = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+    }
+    if (ovf && overflow) atomicOr(overflow, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBvMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (libcuda is not linked: CPU hosts must dlopen us) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (fn == nullptr) {
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    cached.store(fn, std::memory_order_release);
+  }
+  return (EncodeTiledFn)fn;
+}
+
+// planes [B, H, W, C] f16 -> map with box (64 channels, box_w pixels, box_h rows, 1 sample), 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, int batch, int h, int w, int c, int box_w, int box_h, int stride) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return D3B_ERR_CUDA;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  // with a traversal stride s the box spans (n - 1) * s + 1 tensor elements to deliver n of them
+  const cuuint32_t box[4] = {(cuuint32_t)kBvKc, (cuuint32_t)((box_w - 1) * stride + 1), (cuuint32_t)((box_h - 1) * stride + 1), 1u};
+  const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for planes [%d,%d,%d,%d] box [%d,%d] stride %d", (int)r, batch, h, w, c,
+              box_w, box_h, stride);
+    return D3B_ERR_CUDA;
+  }
+  return D3B_OK;
+}
+
+template <int KS, int STRIDE, int COUT>
+static int launch_bev(const d3b_bev16_params* p, const BvGeom& g, cudaStream_t stream) {
+  using Cfg = BvCfg<KS, STRIDE, COUT>;
+  static SmemOptIn optin;
+  D3B_CUDA(ensure_dynamic_smem(bev_conv16_kernel<KS, STRIDE, COUT>, Cfg::kSmemBytes, optin));
+  CUtensorMap tm_hi, tm_lo;
+  int st = make_map(&tm_hi, p->in_hi, p->batch, p->h_in, p->w_in, p->c_in, kBvHalfX, Cfg::kPatchRows, STRIDE);
+  if (st != D3B_OK) return st;
+  st = make_map(&tm_lo, p->in_lo, p->batch, p->h_in, p->w_in, p->c_in, kBvHalfX, Cfg::kPatchRows, STRIDE);
+  if (st != D3B_OK) return st;
+  BvEpi e;
+  e.bias = p->bias; e.scale = p->scale; e.shift = p->shift; e.acc_scale = p->acc_scale; e.relu = p->relu;
+  const int n_tiles = g.batch * g.tiles_y * g.tiles_x * g.groups;
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  bev_conv16_kernel<KS, STRIDE, COUT><<<grid, kBvThreads, Cfg::kSmemBytes, stream>>>(
+      tm_hi, tm_lo, g, (const __half*)p->weight_packed, e, (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, p->overflow);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+
+extern "C" int d3b_bev_conv16(const d3b_bev16_params* p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(p && p->in_hi && p->in_lo && p->weight_packed, "d3b_bev_conv16: null argument");
+  D3B_REQUIRE(p->batch >= 1 && p->h_in >= 1 && p->w_in >= 1 && p->c_in >= 16 && p->c_in % 16 == 0,
+              "d3b_bev_conv16: bad input shape [%d,%d,%d,%d] (C_in must be a multiple of 16)", p->batch, p->h_in, p->w_in, p->c_in);
+  D3B_REQUIRE((p->ksize == 1 || p->ksize == 3) && (p->stride == 1 || p->stride == 2) && !(p->ksize == 1 && p->stride != 1),
+              "d3b_bev_conv16: ksize %d stride %d not built (3x3 s1/s2, 1x1 s1)", p->ksize, p->stride);
+  D3B_REQUIRE(p->pad >= 0 && p->pad <= p->ksize / 2 + 1, "d3b_bev_conv16: pad %d", p->pad);
+  D3B_REQUIRE(p->up >= 1 && p->up <= 4 && p->cgroups >= 1 && p->groups == p->cgroups * p->up * p->up,
+              "d3b_bev_conv16: groups %d != cgroups %d * up^2 (up %d)", p->groups, p->cgroups, p->up);
+  D3B_REQUIRE((p->out_hi != nullptr) == (p->out_lo != nullptr) && (p->out_hi || p->out_f32),
+              "d3b_bev_conv16: give out_hi + out_lo and/or out_f32");
+  D3B_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "d3b_bev_conv16: scale and shift go together");
+  D3B_REQUIRE(p->out_channels % 8 == 0 && p->out_c0 % 8 == 0 && p->out_c0 + p->cgroups * p->c_out <= p->out_channels,
+              "d3b_bev_conv16: output channel slice [%d, %d) does not fit rows of %d", p->out_c0,
+              p->out_c0 + p->cgroups * p->c_out, p->out_channels);
+  BvGeom g;
+  g.batch = p->batch;
+  g.h_out = (p->h_in + 2 * p->pad - p->ksize) / p->stride + 1;
+  g.w_out = (p->w_in + 2 * p->pad - p->ksize) / p->stride + 1;
+  D3B_REQUIRE(g.h_out >= 1 && g.w_out >= 1, "d3b_bev_conv16: empty output grid");
+  g.c_in = p->c_in;
+  g.n_kb = (p->c_in + kBvKc - 1) / kBvKc;
+  g.pad = p->pad;
+  g.tiles_y = div_up(g.h_out, kBvTileY);
+  g.tiles_x = div_up(g.w_out, kBvTileX);
+  g.groups = p->groups; g.cgroups = p->cgroups; g.up = p->up;
+  g.out_h = g.h_out * p->up; g.out_w = g.w_out * p->up;
+  g.out_channels = p->out_channels; g.out_c0 = p->out_c0;
+#define D3B_BEV_CASE(KS, ST)                                                   \
+  if (p->ksize == KS && p->stride == ST) {                                     \
+    switch (p->c_out) {                                                        \
+      case 32: return launch_bev<KS, ST, 32>(p, g, stream);                    \
+      case 64: return launch_bev<KS, ST, 64>(p, g, stream);                    \
+      case 128: return launch_bev<KS, ST, 128>(p, g, stream);                  \
+      default: break;                                                          \
+    }                                                                          \
+  }
+  D3B_BEV_CASE(3, 1)
+  D3B_BEV_CASE(3, 2)
+  D3B_BEV_CASE(1, 1)
+#undef D3B_BEV_CASE
+  set_error("d3b_bev_conv16: C_out per group %d not in {32, 64, 128}", p->c_out);
+  return D3B_ERR_UNSUPPORTED;
+}

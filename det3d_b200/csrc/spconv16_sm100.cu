@@ -1,0 +1,570 @@
+// Output-stationary sparse convolution on tcgen05 with split-f16 operands ("FP16x3"), sm_100a.
+//
+//   out[o,:] = act((sum_k in[nbr[k][o],:] . W[k] + bias) * scale + shift + residual[o,:])
+//
+// Reference: spconv v1.x indice_conv (per offset: gather -> fp32 torch.mm -> scatter-add) followed by
+// BatchNorm1d(eval) / ReLU / residual, call sites det3d/models/backbones/scn.py:73-89,106-157,323-355.
+//
+// Why this form (round 2).  The pair-based kernel (sparse_conv_sm100.cu, D3B_ALGO_TC_PAIRS) sums the offsets' partial
+// products with fp32 atomics: summation order -- hence the last bits -- changed run to run, its 14 launches needed 8
+// buffer-clearing launches and a deferred epilogue, and at lidar densities (~100-160 work items per layer) it was bound
+// by the RED issue rate and two dependent L2 round trips per item.  Here one CTA owns 128 output rows and walks the
+// kernel offsets present in the tile (tile_mask); every offset is one pipeline slot: four groups of gather warps copy
+// the 128 input rows (or zeros where the offset has no neighbour) with 16-byte cp.async straight into a K-major,
+// 128B-swizzled tile, one thread issues the MMAs, accumulation stays in TMEM across all offsets, and the fused
+// bias/BN/residual/ReLU epilogue writes each output row once.  No atomics, fixed summation order: bit-identical
+// results run to run.
+//
+// fp32-equivalent accuracy on the f16 pipe (twice the tf32 rate, half the operand bytes).  Activations live in HBM as
+// two f16 planes, hi = f16(x) and lo = f16(x - hi) (22 significant bits, written once by the producing layer's
+// epilogue); weights are split the same way at load time after an exact power-of-two scaling that keeps their lo
+// parts out of the f16 subnormal range.  D += A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with fp32 accumulation; the dropped
+// lo.lo term is 2^-22 relative.  The three products take TWO MMAs per k-step: B_hi and B_lo are stacked along N
+// ([B_hi | B_lo], N = 2*C_out) so A_hi is read from shared memory once for both, and A_lo x B_hi (N = C_out) lands on
+// the first half of the columns; the epilogue adds the two halves.  |x| >= 65504 cannot be represented: the epilogue
+// raises a device flag instead of silently saturating (the host checks it with the detections).
+//
+// Roles (672 threads): 4 gather groups x 4 warps (slot j -> group j % 4), 1 MMA warp (also owns TMEM), 4 epilogue
+// warps; two TMEM accumulators so the drain of tile t overlaps the MMAs of tile t+1; persistent grid <= 148 CTAs.
+// Algorithmic bytes per layer: N_in*C_in*4 + N_out*C_out*4 + P*8 + K*C_in*C_out*4.
+#include "umma.cuh"
+
+namespace d3b {
+
+constexpr int kOsTileM = 128;
+constexpr int kOsKc = 64;                                  // channels per stage = one 128-byte swizzle row of f16
+constexpr int kOsGroups = 4;
+constexpr int kOsMmaWarp = 4 * kOsGroups;                  // warp 16
+constexpr int kOsEpiWarp0 = kOsMmaWarp + 1;                // warps 17..20 (warp & 3 = 1,2,3,0: one per TMEM quadrant)
+constexpr int kOsThreads = 32 * (kOsEpiWarp0 + 4);         // 672
+constexpr int kOsABytes = kOsTileM * 128;                  // one A plane tile (hi or lo)
+
+template <int COUT>
+struct OsCfg {
+  static constexpr int kBBytes = 2 * COUT * 128;           // [B_hi rows | B_lo rows]
+  static constexpr int kStageBytes = 2 * kOsABytes + kBBytes;
+  static constexpr int kStages = COUT >= 128 ? 3 : 4;
+  static constexpr int kAccCols = 2 * COUT;                // [hi.hi + lo.hi | hi.lo]
+  static constexpr int kTmemCols = 2 * kAccCols;           // double-buffered across tiles (64 .. 512, a power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 32 * kOsTileM * 4;
+};
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// Fused epilogue on 16 consecutive output channels of one row; returns true if a value left the f16 range.
+struct OsEpi {
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const __half* res_hi;
+  const __half* res_lo;
+  float acc_scale;
+  int relu;
+};
+
+__device__ __forceinline__ bool epilogue16(float (&v)[16], const OsEpi& e, size_t row_off, int col, __half* out_hi,
+                                           __half* out_lo, float* out_f32) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] *= e.acc_scale;
+  if (e.bias) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col + q));
+      v[q] += b.x; v[q + 1] += b.y; v[q + 2] += b.z; v[q + 3] += b.w;
+    }
+  }
+  if (e.scale) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(e.scale + col + q));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(e.shift + col + q));
+      v[q] = fmaf(v[q], s.x, t.x); v[q + 1] = fmaf(v[q + 1], s.y, t.y);
+      v[q + 2] = fmaf(v[q + 2], s.z, t.z); v[q + 3] = fmaf(v[q + 3], s.w, t.w);
+    }
+  }
+  if (e.res_hi) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 8) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(e.res_hi + row_off + col + q));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(e.res_lo + row_off + col + q));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+        v[q + 2 * j] += fh.x + fl.x;          // hi + lo is exact in fp32 (22 bits)
+        v[q + 2 * j + 1] += fh.y + fl.y;
+      }
+    }
+  }
+  bool ovf = false;
+  if (e.relu) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+  }
+  if (out_hi) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+      __half h0, l0, h1, l1;
+      split_f16(v[q], h0, l0);
+      split_f16(v[q + 1], h1, l1);
+      hi[q >> 1] = pack_half2(h0, h1);
+      lo[q >> 1] = pack_half2(l0, l1);
+      ovf |= !(fabsf(v[q]) < 65504.f) | !(fabsf(v[q + 1]) < 65504.f);
+    }
+    uint4* ph = reinterpret_cast<uint4*>(out_hi + row_off + col);
+    uint4* pl = reinterpret_cast<uint4*>(out_lo + row_off + col);
+    ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  if (out_f32) {
+    float4* pf = reinterpret_cast<float4*>(out_f32 + row_off + col);
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) pf[q >> 2] = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+  }
+  return ovf;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kOsThreads, 1)
+spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, const int* __restrict__ nbr,
+                   const unsigned int* __restrict__ tile_mask, const int* __restrict__ n_out_p, int out_cap, int c_in,
+                   int n_kb, const __half* __restrict__ packed, OsEpi epi, __half* __restrict__ out_hi,
+                   __half* __restrict__ out_lo, float* __restrict__ out_f32, int* __restrict__ overflow) {
+  using Cfg = OsCfg<COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto acc_full = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
+  auto acc_empty = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+  int* koff_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 128);   // [32] active offsets
+  int* nbr_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);    // [32][128] neighbour rows
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_out = min(*n_out_p, out_cap);
+  const int n_tiles = (n_out + kOsTileM - 1) / kOsTileM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 128 + 1);   // the 128 gather threads of one group + the expect_tx arrive
+      mbar_init(empty_bar(s), 1);        // tcgen05.commit
+    }
+    for (uint32_t b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kOsMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
+  uint32_t tile_it = 0;   // accumulator phase counter
+
+  if (warp < kOsMmaWarp) {
+    // ===================== gather producers =====================
+    const int group = warp >> 2, wq = warp & 3;
+    const int g = lane >> 3, c = lane & 7;
+    const bool issues_tma = (wq == 0 && lane == 0);
+    const int ptid = threadIdx.x;      // 0 .. 511
+    const int c_in_pad = (c_in + 15) & ~15;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row0 = tile * kOsTileM;
+      const unsigned int mask = tile_mask[tile];
+      const int n_off = __popc(mask);
+      const int n_slots = n_off * n_kb;
+
+      // stage nbr[k][row0 .. row0+127] for the active offsets (one global round trip per tile)
+      asm volatile("bar.sync 1, %0;" ::"r"(128 * kOsGroups) : "memory");   // previous tile's readers are done
+      for (int idx = ptid; idx < n_off * kOsTileM; idx += 128 * kOsGroups) {
+        const int n = idx >> 7, r = idx & 127;
+        unsigned int m = mask;
+        for (int t = n; t > 0; --t) m &= m - 1;
+        const int k = __ffs(m) - 1;
+        if (r == 0) koff_s[n] = k;
+        nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)k * out_cap + row0 + r) : -1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(128 * kOsGroups) : "memory");
+
+      for (int j = (int)((group + kOsGroups - (it0 % kOsGroups)) % kOsGroups); j < n_slots; j += kOsGroups) {
+        const int n = j / n_kb, kb = j - n * n_kb;
+        const int ch = kb * kOsKc + c * 8;                 // this thread's 8 channels (16 bytes)
+        const uint32_t it = it0 + (uint32_t)j;
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t stage = smem_base + s * Cfg::kStageBytes;
+        if (issues_tma) {
+          mbar_arrive_expect_tx(full_bar(s), Cfg::kBBytes);
+          tma_bulk_g2s(stage + 2 * kOsABytes, packed + ((size_t)koff_s[n] * n_kb + kb) * (Cfg::kBBytes / 2), Cfg::kBBytes,
+                       full_bar(s));
+        }
+        if (ch < c_in_pad) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int row = wq * 32 + 4 * q + g;
+            const int src = nbr_s[n * kOsTileM + row];
+            const bool live = src >= 0 && ch < c_in;
+            const size_t off = live ? (size_t)src * c_in + ch : 0;
+            const uint32_t dst = stage + sw128_offset(row, c);
+            cp_async16(dst, in_hi + off, live ? 16u : 0u);
+            cp_async16(dst + kOsABytes, in_lo + off, live ? 16u : 0u);
+          }
+        }
+        cp_async_wait_all();
+        fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar(s));
+      }
+      it0 += (uint32_t)n_slots;
+    }
+  } else if (warp == kOsMmaWarp) {
+    // ===================== MMA issuer (one elected lane) =====================
+    constexpr uint32_t idesc2 = umma_idesc_f16(kOsTileM, 2 * COUT);   // A_hi x [B_hi | B_lo]
+    constexpr uint32_t idesc1 = umma_idesc_f16(kOsTileM, COUT);       // A_lo x B_hi
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const unsigned int mask = tile_mask[tile];
+      if (mask == 0) continue;
+      const int n_slots = __popc(mask) * n_kb;
+      const uint32_t buf = tile_it & 1u;
+      mbar_wait(acc_empty(buf), ((tile_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_d + buf * Cfg::kAccCols;
+      uint32_t accumulate = 0;
+      for (int j = 0; j < n_slots; ++j, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1u;
+        const int kb = j % n_kb;
+        const int n_ks = min(kOsKc / 16, (c_in - kb * kOsKc + 15) / 16);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
+          const uint32_t a_lo = a_hi + kOsABytes;
+          const uint32_t b = a_lo + kOsABytes;
+          for (int ks = 0; ks < n_ks; ++ks) {
+            const uint32_t adv = ks * 32;   // 16 f16 = 32 bytes along K inside the swizzle row
+            tc_mma_f16(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b + adv), idesc2, accumulate);
+            tc_mma_f16(d_addr, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b + adv), idesc1, 1u);
+            accumulate = 1u;
+          }
+          tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+        }
+        __syncwarp();
+        accumulate = 1u;
+      }
+      if (lane == 0) tc_commit(acc_full(buf));
+      __syncwarp();
+      ++tile_it;
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> fused bias/BN/residual/ReLU -> f16 planes =====================
+    const int quad = warp & 3;
+    bool ovf = false;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const bool any = tile_mask[tile] != 0u;
+      const int o = tile * kOsTileM + quad * 32 + lane;
+      const uint32_t buf = tile_it & 1u;
+      if (any) {
+        mbar_wait(acc_full(buf), (tile_it >> 1) & 1u);
+        tc_fence_after();
+      }
+      const uint32_t t0 = tmem_d + buf * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        float v[16];
+        if (any) {
+          uint32_t r1[16], r2[16];
+          tc_ld16_nowait(t0 + c0, r1);
+          tc_ld16_nowait(t0 + COUT + c0, r2);
+          tc_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r1[q]) + __uint_as_float(r2[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        }
+        if (o < n_out) ovf |= epilogue16(v, epi, (size_t)o * COUT, c0, out_hi, out_lo, out_f32);
+      }
+      if (any) {
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));
+        ++tile_it;
+      }
+    }
+    if (ovf && overflow) atomicOr(overflow, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kOsMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- first layer: fp32 rows with a handful of channels (C_in <= 16: the voxel mean, 4 or 5 features) -----------------
+// 2*27*C_in*C_out flops per row -- nothing for the tensor cores.  fp32 FFMA, output-stationary, same epilogue and
+// output format as the tcgen05 kernel.  Four lanes share a row (16 output channels each at C_out = 64).
+template <int COUT>
+__global__ void __launch_bounds__(256)
+spconv_first16_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr, const int* __restrict__ n_out_p,
+                      int out_cap, int c_in, int k_vol, const float* __restrict__ weight, OsEpi epi,
+                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32,
+                      int* __restrict__ overflow) {
+  extern __shared__ float w_s[];                 // [k_vol][c_in][COUT]
+  for (int i = threadIdx.x; i < k_vol * c_in * COUT; i += blockDim.x) w_s[i] = weight[i];
+  __syncthreads();
+  constexpr int kParts = COUT / 16;              // threads per row
+  const int n_out = min(*n_out_p, out_cap);
+  const long long total = (long long)n_out * kParts;
+  bool ovf = false;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(e / kParts), col = (int)(e % kParts) * 16;
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+    for (int k = 0; k < k_vol; ++k) {
+      const int src = __ldg(nbr + (size_t)k * out_cap + o);
+      if (src < 0) continue;
+      for (int ci = 0; ci < c_in; ++ci) {
+        const float a = __ldg(feat_in + (size_t)src * c_in + ci);
+        const float* w = w_s + ((size_t)k * c_in + ci) * COUT + col;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = fmaf(a, w[q], acc[q]);
+      }
+    }
+    ovf |= epilogue16(acc, epi, (size_t)o * COUT, col, out_hi, out_lo, out_f32);
+  }
+  if (ovf && overflow) atomicOr(overflow, 1);
+}
+
+// ---- f16 weight image ------------------------------------------------------------------------------------------------
+// packed[k][kb][part][n][swizzled 64 halves], part 0 = hi, 1 = lo of w * 2^w_exp; zero beyond c_in.
+__global__ void __launch_bounds__(256)
+pack_weight16_kernel(const float* __restrict__ w, int c_in, int c_out, int k_vol, int n_kb, float w_mul,
+                     __half* __restrict__ packed) {
+  const long long total = (long long)k_vol * n_kb * 2 * c_out * kOsKc;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long t = e;
+    const int cc = (int)(t % kOsKc); t /= kOsKc;
+    const int n = (int)(t % c_out); t /= c_out;
+    const int part = (int)(t % 2); t /= 2;
+    const int kb = (int)(t % n_kb); t /= n_kb;
+    const int k = (int)t;
+    const int ci = kb * kOsKc + cc;
+    const float x = ci < c_in ? w[((size_t)k * c_in + ci) * c_out + n] * w_mul : 0.0f;
+    __half hi, lo;
+    split_f16(x, hi, lo);
+    const size_t tile = (((size_t)k * n_kb + kb) * 2 + part) * (size_t)(c_out * kOsKc);
+    const uint32_t off = sw128_offset(n, cc >> 3) + (cc & 7) * 2;     // bytes
+    packed[tile + off / 2] = part == 0 ? hi : lo;
+  }
+}
+
+// ---- plane <-> fp32 conversions (API boundary, tests) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ hi, __half* __restrict__ lo,
+               int* __restrict__ overflow) {
+  bool ovf = false;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float v = x[e];
+    __half h, l;
+    split_f16(v, h, l);
+    hi[e] = h;
+    lo[e] = l;
+    ovf |= !(fabsf(v) < 65504.f);
+  }
+  if (ovf && overflow) atomicOr(overflow, 1);
+}
+
+__global__ void __launch_bounds__(256)
+merge16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n, float* __restrict__ x) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    x[e] = __half2float(hi[e]) + __half2float(lo[e]);
+}
+
+// rows (f16 planes or fp32) -> channels-last BEV planes [B*H*W, C*D] (pre-zeroed), channel = c*D + z: the values of
+// `dense.view(B, C*D, H, W)` (scn.py:192-195) in NHWC order.
+__global__ void __launch_bounds__(256)
+sparse_to_bev16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, const float* __restrict__ in_f32,
+                       const int* __restrict__ coors, const int* __restrict__ n_rows, int row_cap, int C, int D, int H,
+                       int W, int B, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int n = min(*n_rows, row_cap);
+  const long long total = (long long)n * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / C), c = (int)(e - (long long)r * C);
+    const int4 q = *reinterpret_cast<const int4*>(coors + (size_t)r * 4);
+    if ((unsigned)q.x >= (unsigned)B || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
+        (unsigned)q.w >= (unsigned)W)
+      continue;
+    const size_t dst = (((size_t)q.x * H + q.z) * W + q.w) * ((size_t)C * D) + (size_t)c * D + q.y;
+    if (in_f32) {
+      __half h, l;
+      split_f16(in_f32[e], h, l);
+      out_hi[dst] = h;
+      out_lo[dst] = l;
+    } else {
+      out_hi[dst] = in_hi[e];
+      out_lo[dst] = in_lo[e];
+    }
+  }
+}
+
+static bool os16_shape_ok(int c_in, int c_out) {
+  const bool cin_ok = c_in >= 8 && c_in <= 512 && c_in % 8 == 0;    // rows are gathered in 16-byte chunks
+  const bool cout_ok = c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128;
+  return cin_ok && cout_ok;
+}
+
+static OsEpi epi_of(const d3b_conv16_params* p) {
+  OsEpi e;
+  e.bias = p->bias; e.scale = p->scale; e.shift = p->shift;
+  e.res_hi = (const __half*)p->residual_hi; e.res_lo = (const __half*)p->residual_lo;
+  e.acc_scale = p->acc_scale; e.relu = p->relu;
+  return e;
+}
+
+template <int COUT>
+static int launch_os16(const d3b_conv16_params* p, const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out,
+                       int32_t out_cap, cudaStream_t stream) {
+  using Cfg = OsCfg<COUT>;
+  static SmemOptIn optin;
+  D3B_CUDA(ensure_dynamic_smem(spconv_os16_kernel<COUT>, Cfg::kSmemBytes, optin));
+  const int n_tiles = div_up(out_cap, kOsTileM);
+  const int grid = n_tiles < kNumSMs ? (n_tiles > 0 ? n_tiles : 1) : kNumSMs;
+  const int n_kb = (p->c_in + kOsKc - 1) / kOsKc;
+  spconv_os16_kernel<COUT><<<grid, kOsThreads, Cfg::kSmemBytes, stream>>>(
+      (const __half*)p->in_hi, (const __half*)p->in_lo, nbr, tile_mask, n_out, out_cap, p->c_in, n_kb,
+      (const __half*)p->weight_packed, epi_of(p), (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, p->overflow);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+template <int COUT>
+static int launch_first16(const d3b_conv16_params* p, const int32_t* nbr, const int32_t* n_out, int32_t out_cap,
+                          cudaStream_t stream) {
+  const size_t smem = (size_t)p->k_vol * p->c_in * COUT * sizeof(float);
+  static SmemOptIn optin;
+  D3B_REQUIRE(smem <= 160 * 1024, "first-layer sparse conv: weights (%zu bytes) do not fit in shared memory", smem);
+  D3B_CUDA(ensure_dynamic_smem(spconv_first16_kernel<COUT>, smem, optin));
+  const int grid = grid_for((long long)out_cap * (COUT / 16), 256, 4);
+  spconv_first16_kernel<COUT><<<grid, 256, smem, stream>>>(p->in_f32, nbr, n_out, out_cap, p->c_in, p->k_vol, p->weight,
+                                                         epi_of(p), (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32,
+                                                         p->overflow);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+
+extern "C" size_t d3b_conv16_packed_weight_halves(int32_t c_in, int32_t c_out, int32_t k_vol) {
+  if (c_in < 1 || c_in > 512 || k_vol < 1 || k_vol > 32) return 0;
+  if (!(c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128)) return 0;
+  const int n_kb = (c_in + kOsKc - 1) / kOsKc;
+  return (size_t)k_vol * n_kb * 2 * c_out * kOsKc;
+}
+
+extern "C" int d3b_conv16_pack_weight(const float* weight_dev, int32_t c_in, int32_t c_out, int32_t k_vol,
+                                      int32_t w_exp, void* packed_dev, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(weight_dev && packed_dev, "d3b_conv16_pack_weight: null argument");
+  D3B_REQUIRE(w_exp >= -60 && w_exp <= 60, "d3b_conv16_pack_weight: w_exp %d outside [-60, 60]", w_exp);
+  const size_t n = d3b_conv16_packed_weight_halves(c_in, c_out, k_vol);
+  if (n == 0) {
+    set_error("d3b_conv16_pack_weight: unsupported C_in=%d C_out=%d k_vol=%d", c_in, c_out, k_vol);
+    return D3B_ERR_UNSUPPORTED;
+  }
+  const int n_kb = (c_in + kOsKc - 1) / kOsKc;
+  pack_weight16_kernel<<<grid_for((long long)n, 256), 256, 0, stream>>>(weight_dev, c_in, c_out, k_vol, n_kb,
+                                                                        ldexpf(1.0f, w_exp), (__half*)packed_dev);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+extern "C" int d3b_sparse_conv16(const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out, int32_t out_cap,
+                                 const d3b_conv16_params* p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(nbr && n_out && p, "d3b_sparse_conv16: null argument");
+  D3B_REQUIRE(p->k_vol >= 1 && p->k_vol <= 32 && out_cap >= 0, "d3b_sparse_conv16: bad shape (k_vol %d)", p->k_vol);
+  D3B_REQUIRE((p->out_hi != nullptr) == (p->out_lo != nullptr) && (p->out_hi || p->out_f32),
+              "d3b_sparse_conv16: give out_hi + out_lo and/or out_f32");
+  D3B_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "d3b_sparse_conv16: scale and shift go together");
+  D3B_REQUIRE((p->residual_hi == nullptr) == (p->residual_lo == nullptr), "d3b_sparse_conv16: residual planes go together");
+  if (out_cap == 0) return D3B_OK;
+  if (p->in_f32) {      // first layer: fp32 rows, few channels
+    D3B_REQUIRE(p->weight && p->c_in >= 1 && p->c_in <= 16, "d3b_sparse_conv16: fp32-input layers need weight and C_in <= 16");
+    switch (p->c_out) {
+      case 16: return launch_first16<16>(p, nbr, n_out, out_cap, stream);
+      case 32: return launch_first16<32>(p, nbr, n_out, out_cap, stream);
+      case 64: return launch_first16<64>(p, nbr, n_out, out_cap, stream);
+      default:
+        set_error("d3b_sparse_conv16: fp32-input layer with C_out=%d (16/32/64 built)", p->c_out);
+        return D3B_ERR_UNSUPPORTED;
+    }
+  }
+  D3B_REQUIRE(tile_mask && p->in_hi && p->in_lo && p->weight_packed, "d3b_sparse_conv16: null planes / tile_mask / packed weights");
+  if (!os16_shape_ok(p->c_in, p->c_out)) {
+    set_error("d3b_sparse_conv16: unsupported C_in=%d C_out=%d", p->c_in, p->c_out);
+    return D3B_ERR_UNSUPPORTED;
+  }
+  switch (p->c_out) {
+    case 16: return launch_os16<16>(p, nbr, tile_mask, n_out, out_cap, stream);
+    case 32: return launch_os16<32>(p, nbr, tile_mask, n_out, out_cap, stream);
+    case 64: return launch_os16<64>(p, nbr, tile_mask, n_out, out_cap, stream);
+    default: return launch_os16<128>(p, nbr, tile_mask, n_out, out_cap, stream);
+  }
+}
+
+extern "C" int d3b_split16(const float* x, int64_t n, void* hi, void* lo, int32_t* overflow, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(n >= 0 && (n == 0 || (x && hi && lo)), "d3b_split16: null argument");
+  if (n == 0) return D3B_OK;
+  split16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, n, (__half*)hi, (__half*)lo, overflow);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+extern "C" int d3b_merge16(const void* hi, const void* lo, int64_t n, float* x, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(n >= 0 && (n == 0 || (x && hi && lo)), "d3b_merge16: null argument");
+  if (n == 0) return D3B_OK;
+  merge16_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const __half*)hi, (const __half*)lo, n, x);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
+extern "C" int d3b_sparse_to_bev16(const void* in_hi, const void* in_lo, const float* in_f32, const int32_t* coors,
+                                   const int32_t* n_rows, int32_t row_cap, int32_t channels, const int32_t spatial[3],
+                                   int32_t batch, void* out_hi, void* out_lo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  D3B_REQUIRE(coors && n_rows && spatial && out_hi && out_lo, "d3b_sparse_to_bev16: null argument");
+  D3B_REQUIRE((in_f32 != nullptr) != (in_hi != nullptr && in_lo != nullptr), "d3b_sparse_to_bev16: give fp32 rows OR both planes");
+  D3B_REQUIRE(channels >= 1 && batch >= 1 && row_cap >= 0, "d3b_sparse_to_bev16: bad shape");
+  if (row_cap == 0) return D3B_OK;
+  sparse_to_bev16_kernel<<<grid_for((long long)row_cap * channels, 256), 256, 0, stream>>>(
+      (const __half*)in_hi, (const __half*)in_lo, in_f32, coors, n_rows, row_cap, channels, spatial[0], spatial[1],
+      spatial[2], batch, (__half*)out_hi, (__half*)out_lo);
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}

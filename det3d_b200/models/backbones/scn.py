@@ -134,6 +134,17 @@ class _SparseMiddleEncoder(nn.Module):
         _d, h, w = fused._state["final_level"].spatial
         return rows, (int(batch_size), h, w)
 
+    def forward_planes(self, voxel_features, coors, batch_size, input_shape, n_dev=None, overflow=None):
+        """NHWC split-f16 planes [B, H, W, C*D] of the BEV map (the FP16x3 dense path's input): the same values as
+        forward()'s [B, C*D, H, W]."""
+        if self.training:
+            raise RuntimeError("det3d_b200 middle encoders are inference-only: call .eval()")
+        sparse_shape = [int(v) for v in (np.array(input_shape[::-1]) + [1, 0, 0])]
+        fused = self.fused()
+        if overflow is not None:
+            fused.external_overflow = overflow
+        return fused.run(voxel_features, coors.int(), int(batch_size), sparse_shape, n_dev=n_dev, bev_rows="planes")
+
     def forward_unfused(self, voxel_features, coors, batch_size, input_shape):
         """Layer-by-layer path through the spconv-style modules (API parity / cross-check)."""
         sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]

@@ -132,6 +132,29 @@ class PointPillarsScatter(nn.Module):
     def init_weights(self, pretrained=None):
         pass
 
+    def forward_planes(self, voxel_features, coords, batch_size, input_shape, n_dev=None):
+        """[M, C] pillar features + coords -> NHWC split-f16 planes [B, ny, nx, C] (the FP16x3 dense path's input);
+        the canvas of pillar_encoder.py:175-211 in channels-last layout, split on the way."""
+        from det3d_b200.ops.spconv import conv16, core
+        nx, ny = int(input_shape[0]), int(input_shape[1])
+        feats = voxel_features.to(torch.float32).contiguous()
+        m = feats.shape[0]
+        coords = coords.to(torch.int32).contiguous()
+        if n_dev is None:
+            n = torch.tensor([m, m], dtype=torch.int32, device=feats.device)
+        else:
+            n = torch.cat([n_dev.reshape(-1)[:1].to(torch.int32)] * 2)
+        key = (batch_size, ny, nx, feats.device)
+        cache = self.__dict__.setdefault("_planes", {})
+        out = cache.get(key)
+        if out is None:
+            out = cache[key] = conv16.Planes((batch_size, ny, nx, self.nchannels), feats.device)
+        out.zero_()
+        if m > 0:
+            level = core.SparseLevel(coords, n, m, (1, ny, nx), batch_size)
+            conv16.sparse_to_bev16(feats, level, out)
+        return out
+
     def forward(self, voxel_features, coords, batch_size, input_shape, n_dev=None):
         """[M, C] pillar features + coords [M,4] (b, z, y, x) -> [B, C, ny, nx] (pillar_encoder.py:175-211)."""
         from det3d_b200.ops.spconv import core

@@ -79,8 +79,9 @@ def rpn_is_fusable(rpn):
         return False
 
 
-class FusedBevStack:
-    """RPN + all task heads as a chain of channels-last tensor-core convs."""
+class FusedBevStackTF32:
+    """Round-1 path (3xTF32 through the sparse gather kernel, stride-1 RPN only); kept as the fallback when a
+    feature leaves the f16 range and as an in-library cross-check of `FusedBevStack`."""
 
     def __init__(self, rpn, head):
         self.rpn, self.head = rpn, head
@@ -179,5 +180,189 @@ class FusedBevStack:
             for name, c in names:
                 d[name] = flat[..., col:col + c]
                 col += c
+            preds.append(d)
+        return preds
+
+
+# ======================================================================================================
+# FP16x3 path: the whole RPN (any block strides / ConvTranspose deblocks / concat) + all task heads on
+# NHWC f16 planes through TMA tensor maps (csrc/bevconv16_sm100.cu).
+# ======================================================================================================
+from . import conv16  # noqa: E402
+
+
+def _conv_bn_relu(seq, i):
+    """(conv, bn | None, relu, next index) for the conv module at seq[i]."""
+    conv = seq[i]
+    j = i + 1
+    bn = None
+    if j < len(seq) and isinstance(seq[j], nn.modules.batchnorm._BatchNorm):
+        bn = seq[j]
+        j += 1
+    relu = j < len(seq) and isinstance(seq[j], nn.ReLU)
+    if relu:
+        j += 1
+    return conv, bn, relu, j
+
+
+def _layer16(conv, bn, relu, extra_pad, device):
+    if bn is not None and bn.training:
+        raise RuntimeError("fused BEV stack is inference-only: call .eval()")
+    scale = shift = None
+    if bn is not None:
+        scale, shift = _bn_fold(bn)
+    bias = None if conv.bias is None else conv.bias.detach().float()
+    if isinstance(conv, nn.ConvTranspose2d):
+        s = int(conv.stride[0])
+        assert tuple(conv.kernel_size) == (s, s) and tuple(conv.stride) == (s, s) and tuple(conv.padding) == (0, 0)
+        w = conv.weight.detach().float()                     # [C_in, C_out, s, s]
+        wk = w.permute(2, 3, 0, 1).reshape(s * s, 1, w.shape[0], w.shape[1])
+        return conv16.BevConv16(wk, 1, up=s, bias=bias, scale=scale, shift=shift, relu=relu, device=device)
+    kh, kw = conv.kernel_size
+    st = int(conv.stride[0])
+    pad = int(conv.padding[0]) + extra_pad
+    assert kh == kw and tuple(conv.stride) == (st, st) and int(conv.padding[1]) + extra_pad == pad
+    return conv16.BevConv16(_conv2d_weight(conv), kh, stride=st, pad=pad, bias=bias, scale=scale, shift=shift, relu=relu,
+                            device=device)
+
+
+def rpn_is_fusable16(rpn):
+    """Every RPN the reference builds (necks/rpn.py:82-143): 3x3 blocks with stride 1 or 2, deblocks that are 1x1 convs
+    or ConvTranspose2d(kernel = stride); channel counts multiples of 16."""
+    try:
+        for blk in rpn.blocks:
+            for m in blk:
+                if isinstance(m, nn.Conv2d):
+                    if m.kernel_size != (3, 3) or m.stride not in ((1, 1), (2, 2)) or m.in_channels % 16 or m.groups != 1:
+                        return False
+                elif not isinstance(m, (nn.ZeroPad2d, nn.ReLU, nn.modules.batchnorm._BatchNorm)):
+                    return False
+        for blk in rpn.deblocks:
+            for m in blk:
+                if isinstance(m, nn.ConvTranspose2d):
+                    if m.kernel_size != m.stride or m.stride[0] != m.stride[1] or m.stride[0] > 4 or m.in_channels % 16:
+                        return False
+                elif isinstance(m, nn.Conv2d):
+                    if m.kernel_size != (1, 1) or m.stride != (1, 1) or m.in_channels % 16:
+                        return False
+                elif not isinstance(m, (nn.ReLU, nn.modules.batchnorm._BatchNorm)):
+                    return False
+        ok_width = all(int(c) in (32, 64, 128) or int(c) % 128 == 0 for c in rpn._num_upsample_filters)
+        return len(rpn.deblocks) >= 1 and ok_width       # a deblock fills whole channel blocks of its concat slice
+    except AttributeError:
+        return False
+
+
+class FusedBevStack:
+    """RPN + all task heads on NHWC f16 planes (FP16x3): one launch per conv layer, the deblocks write straight into
+    their channel slice of the concat buffer, and the heads of all tasks are ONE 1x1 conv whose fp32 output rows are
+    already the NHWC-permuted layout `Head.forward` produces (mg_head.py:214-230)."""
+
+    def __init__(self, rpn, head):
+        self.rpn, self.head = rpn, head
+        self._sig = None
+        self._plan = None
+        self._bufs = {}
+
+    def _signature(self):
+        ts = [p for p in self.rpn.parameters()] + [b for b in self.rpn.buffers()] + [p for p in self.head.tasks.parameters()]
+        return tuple((t._version, t.data_ptr()) for t in ts)
+
+    def _compile(self, device):
+        rpn = self.rpn
+        start = rpn._upsample_start_idx
+        blocks = []
+        for blk in rpn.blocks:
+            seq, layers, i, pad = list(blk), [], 0, 0
+            while i < len(seq):
+                m = seq[i]
+                if isinstance(m, nn.ZeroPad2d):
+                    pad = int(m.padding[0])
+                    i += 1
+                elif isinstance(m, nn.Conv2d):
+                    conv, bn, relu, i = _conv_bn_relu(seq, i)
+                    layers.append(_layer16(conv, bn, relu, pad, device))
+                    pad = 0
+                else:
+                    i += 1
+            blocks.append(layers)
+        deblocks = []
+        for blk in rpn.deblocks:
+            seq = list(blk)
+            conv, bn, relu, _ = _conv_bn_relu(seq, 0)
+            deblocks.append(_layer16(conv, bn, relu, 0, device))
+        # heads: one 1x1 conv over the concatenated output channels of every task
+        ws, bs, self._splits = [], [], []
+        for task in self.head.tasks:
+            parts = [("box_preds", task.conv_box), ("cls_preds", task.conv_cls)]
+            if task.use_dir:
+                parts.append(("dir_cls_preds", task.conv_dir))
+            names = []
+            for name, conv in parts:
+                ws.append(_conv2d_weight(conv))
+                bs.append(conv.bias.detach().float())
+                names.append((name, conv.out_channels))
+            self._splits.append(names)
+        heads = conv16.BevConv16(torch.cat(ws, dim=2), 1, bias=torch.cat(bs), relu=False, device=device)
+        self._plan = dict(blocks=blocks, deblocks=deblocks, heads=heads, start=start,
+                          concat=sum(d.c_out_total for d in deblocks))
+
+    def _planes(self, key, shape, device):
+        p = self._bufs.get(key)
+        if p is None or p.shape != tuple(shape):
+            p = self._bufs[key] = conv16.Planes(shape, device)
+        return p
+
+    def layers(self):
+        """Flat (tag, layer) list in execution order (bench / accounting)."""
+        out = []
+        for i, blk in enumerate(self._plan["blocks"]):
+            out += [("block%d.%d" % (i, j), l) for j, l in enumerate(blk)]
+            if i - self._plan["start"] >= 0:
+                out.append(("deblock%d" % (i - self._plan["start"]), self._plan["deblocks"][i - self._plan["start"]]))
+        out.append(("heads", self._plan["heads"]))
+        return out
+
+    def run(self, x, overflow=None):
+        """x: Planes [B, H, W, C] -> list (per task) of dicts like Head.forward: box_preds [B,H',W',a*code],
+        cls_preds [B,H',W',a*cls], dir_cls_preds [B,H',W',a*2] (fp32 views of one output buffer)."""
+        device = x.device
+        with _lib.on_device_of(x.buf):
+            sig = self._signature()
+            if self._plan is None or sig != self._sig:
+                self._compile(device)
+                self._sig = sig
+            pl = self._plan
+            b = x.shape[0]
+            concat = None
+            col = 0
+            for i, blk in enumerate(pl["blocks"]):
+                for j, layer in enumerate(blk):
+                    ho, wo = layer.out_hw(x.shape[1], x.shape[2])
+                    out = self._planes(("blk", i, j % 2), (b, ho, wo, layer.c_out_padded), device)
+                    layer(x, out=out, overflow=overflow, tag="bev3x3" if layer.ksize == 3 else "bev1x1")
+                    x = out
+                k = i - pl["start"]
+                if k >= 0:
+                    de = pl["deblocks"][k]
+                    ho, wo = de.out_hw(x.shape[1], x.shape[2])
+                    if concat is None:
+                        concat = self._planes(("concat",), (b, ho, wo, pl["concat"]), device)
+                    assert tuple(concat.shape[1:3]) == (ho, wo), "deblock outputs must share one grid"
+                    de(x, out=concat, out_c0=col, overflow=overflow, tag="deblock")
+                    col += de.c_out_total
+            heads = pl["heads"]
+            hc, wc = concat.shape[1], concat.shape[2]
+            key = ("heads", b, hc, wc)
+            out32 = self._bufs.get(key)
+            if out32 is None:
+                out32 = self._bufs[key] = torch.empty((b, hc, wc, heads.c_out_padded), dtype=torch.float32, device=device)
+            heads(concat, out_f32=out32, tag="heads")
+        preds, c0 = [], 0
+        for names in self._splits:
+            d = {}
+            for name, c in names:
+                d[name] = out32[..., c0:c0 + c]
+                c0 += c
             preds.append(d)
         return preds

@@ -12,12 +12,12 @@ import torch
 from torch import nn
 
 from ... import _lib
-from . import core
+from . import conv16, core
 from .modules import SparseConvolution
 
 
 class _Layer:
-    __slots__ = ("conv", "bn", "relu", "residual", "save_identity", "cw", "sig")
+    __slots__ = ("conv", "bn", "relu", "residual", "save_identity", "cw", "sig", "cw16", "sig16")
 
     def __init__(self, conv, bn, relu, residual=False, save_identity=False):
         self.conv, self.bn, self.relu = conv, bn, relu
@@ -25,6 +25,8 @@ class _Layer:
         self.save_identity = save_identity  # this layer's INPUT is a block input
         self.cw = None
         self.sig = None
+        self.cw16 = None
+        self.sig16 = None
 
 
 def _bn_fold(bn):
@@ -77,7 +79,16 @@ class FusedSparseEncoder:
     def __init__(self, middle_conv):
         self.plan = compile_plan(middle_conv)
         self._state = None
-        self.algo_override = None  # testing hook: force SIMT / TC for every layer
+        # "fp16x3" (default): output-stationary tcgen05 kernels on split-f16 planes (csrc/spconv16_sm100.cu) --
+        # deterministic, fused epilogues, no atomics.  "tf32x3": the round-1 kernels (pair-based + fp32 atomics, or
+        # output-stationary with deterministic=True); also the fallback when a feature leaves the f16 range.
+        self.math = "fp16x3"
+        self.external_overflow = None   # int32[1] device flag shared with the rest of the model (else a private one)
+        self.algo_override = None  # testing hook (tf32x3 path): force SIMT / TC for every layer
+        # deterministic=True runs every layer output-stationary (D3B_ALGO_TC: one CTA owns an output tile, fixed
+        # summation order, no atomics) -> bit-identical results run to run; the default pair-based kernel sums the
+        # offsets' partial products with fp32 atomics, whose order varies
+        self.deterministic = False
         self.overlap_rulebooks = True   # build the rulebook chain on a side stream (see run)
 
     # ---- parameters ------------------------------------------------------------
@@ -86,7 +97,7 @@ class FusedSparseEncoder:
             tensors = [L.conv.weight, L.conv.bias]
             if L.bn is not None:
                 tensors += [L.bn.weight, L.bn.bias, L.bn.running_mean, L.bn.running_var]
-            sig = tuple((None if t is None else (t._version, t.data_ptr())) for t in tensors) + (self.algo_override,)
+            sig = tuple((None if t is None else (t._version, t.data_ptr())) for t in tensors) + (self.algo_override, self.deterministic)
             if L.cw is not None and L.sig == sig:
                 continue
             if L.bn is not None and L.bn.training:
@@ -97,7 +108,8 @@ class FusedSparseEncoder:
                 scale, shift = scale.to(device), shift.to(device)
             algo = self.algo_override
             if algo is None:   # sparse levels: compacted pairs on the tensor cores whenever the shape allows
-                algo = _lib.ALGO_TC_PAIRS if core.tc_supported(L.conv.in_channels, L.conv.out_channels) else _lib.ALGO_SIMT
+                tc = _lib.ALGO_TC if self.deterministic else _lib.ALGO_TC_PAIRS
+                algo = tc if core.tc_supported(L.conv.in_channels, L.conv.out_channels) else _lib.ALGO_SIMT
             L.cw = core.ConvWeights(
                 L.conv.weight.to(device), bias=None if L.conv.bias is None else L.conv.bias.to(device),
                 scale=scale, shift=shift, relu=L.relu, algo=algo,
@@ -172,6 +184,10 @@ class FusedSparseEncoder:
         if (st is None or st["cap0"] < cap_needed or st["batch"] != batch_size
                 or st["spatial"] != tuple(spatial) or st["device"] != device):
             st = self._state = self._build_state(cap_needed, spatial, batch_size, device)
+        if self.math == "fp16x3" and self.algo_override is None:
+            return self._run16(st, features, coors, batch_size, n_dev, bev_rows)
+        if bev_rows == "planes":
+            raise ValueError("BEV planes are produced by the fp16x3 path only")
         self._refresh_weights(device)
         lvl0 = st["level0"]
         # adopt the caller's coordinate rows (zero-copy) for this run
@@ -274,6 +290,130 @@ class FusedSparseEncoder:
         core.sparse_to_dense(x, st["final_level"], out=dense)
         return dense
 
+    # ---- FP16x3 path ------------------------------------------------------------------------
+    def _refresh_weights16(self, device):
+        for L in self.plan:
+            tensors = [L.conv.weight, L.conv.bias]
+            if L.bn is not None:
+                tensors += [L.bn.weight, L.bn.bias, L.bn.running_mean, L.bn.running_var]
+            sig = tuple((None if t is None else (t._version, t.data_ptr())) for t in tensors)
+            if L.cw16 is not None and L.sig16 == sig:
+                continue
+            if L.bn is not None and L.bn.training:
+                raise RuntimeError("det3d_b200 sparse encoders are inference-only: call .eval() first")
+            scale = shift = None
+            if L.bn is not None:
+                scale, shift = _bn_fold(L.bn)
+                scale, shift = scale.to(device), shift.to(device)
+            L.cw16 = conv16.ConvWeights16(L.conv.weight.to(device), bias=None if L.conv.bias is None else L.conv.bias.to(device),
+                                          scale=scale, shift=shift, relu=L.relu)
+            L.sig16 = sig
+
+    @staticmethod
+    def _take16(pools, cap, c, busy, device):
+        pool = pools.setdefault(("p16", cap, c), [])
+        for t in pool:
+            if all(t is not b for b in busy):
+                return t
+        t = conv16.Planes((max(cap, 1), c), device)
+        pool.append(t)
+        return t
+
+    def overflowed(self):
+        """True if a feature left the f16 range since the last call (synchronises; the flag is then cleared).
+        The caller must re-run with math='tf32x3' -- nothing was saturated silently."""
+        st = self._state
+        flag = self.external_overflow if self.external_overflow is not None else (st or {}).get("overflow")
+        if flag is None:
+            return False
+        hit = bool(int(flag.item()))
+        if hit:
+            flag.zero_()
+        return hit
+
+    def _run16(self, st, features, coors, batch_size, n_dev, bev_rows):
+        device = features.device
+        m = features.shape[0]
+        self._refresh_weights16(device)
+        lvl0 = st["level0"]
+        coors = coors.to(torch.int32).contiguous()
+        feats = features.to(torch.float32).contiguous()
+        if m == 0:
+            feats = torch.zeros((1, features.shape[1]), dtype=torch.float32, device=device)
+        if m > 0:
+            lvl0.coors[:m].copy_(coors)
+        if n_dev is None:
+            lvl0.n.fill_(m)
+        else:
+            lvl0.n[:1].copy_(n_dev.reshape(-1)[:1].to(torch.int32))
+            lvl0.n[1:2].copy_(lvl0.n[:1])
+        lvl0.rebuild_index()
+        ovf = self.external_overflow
+        if ovf is None:
+            ovf = st.get("overflow")
+            if ovf is None:
+                ovf = st["overflow"] = torch.zeros(1, dtype=torch.int32, device=device)
+
+        # rulebooks depend on coordinates only: the chain of all levels runs on a side stream (fork / join through
+        # events, kept as parallel branches inside a CUDA graph) while the main stream convolves the levels already indexed
+        main = torch.cuda.current_stream(device)
+        ready = {}
+        builds = [(rb, build) for _L, rb, build in st["steps"] if build is not None]
+        if self.overlap_rulebooks and len(builds) > 1:
+            side = st.get("side_stream")
+            if side is None:
+                side = st["side_stream"] = torch.cuda.Stream(device=device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for rb, build in builds:
+                    build(rb, with_pairs=False)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    ready[id(rb)] = ev
+            builds = []
+        waited = set()
+
+        first = self.plan[0].cw16
+        x = feats if first.fp32_input else conv16.Planes.from_f32(feats, ovf)
+        identity = None
+        x_level = lvl0
+        for L, rb, build in st["steps"]:
+            if build is not None and builds:
+                build(rb, with_pairs=False)
+            if id(rb) in ready and id(rb) not in waited:
+                main.wait_event(ready[id(rb)])
+                waited.add(id(rb))
+            if L.save_identity:
+                identity = x
+            out = self._take16(st["pools"], rb.out_level.cap, L.conv.out_channels, (x, identity), device)
+            conv16.sparse_conv16(x, rb, L.cw16, out, residual=identity if L.residual else None, overflow=ovf)
+            if L.residual:
+                identity = None
+            x, x_level = out, rb.out_level
+        final = st["final_level"]
+        d, h, w = final.spatial
+        c = x.shape[-1]
+        if bev_rows:
+            planes = st.get("bev_planes")
+            if planes is None:
+                planes = st["bev_planes"] = conv16.Planes((batch_size, h, w, c * d), device)
+            planes.zero_()
+            conv16.sparse_to_bev16(x, final, planes)
+            if bev_rows == "planes":
+                return planes
+            rows = st.get("bev_rows")
+            if rows is None:
+                rows = st["bev_rows"] = torch.empty((batch_size * h * w, c * d), dtype=torch.float32, device=device)
+            return planes.view(batch_size * h * w, c * d).to_f32(out=rows)
+        rows32 = st.get("final_f32")
+        if rows32 is None:
+            rows32 = st["final_f32"] = torch.empty((max(final.cap, 1), c), dtype=torch.float32, device=device)
+        x.to_f32(out=rows32)
+        dense = st["dense"]
+        dense.zero_()
+        core.sparse_to_dense(rows32, final, out=dense)
+        return dense
+
     def accounting(self):
         """Algorithmic bytes / flops of the most recent run (SURVEY 8d formulas; synchronises).
 
@@ -292,7 +432,7 @@ class FusedSparseEncoder:
             b = n_in * cin * 4 + n_out * cout * 4 + pairs * 8 + k * cin * cout * 4
             f = 2 * pairs * cin * cout
             layers.append(dict(n_in=n_in, n_out=n_out, pairs=pairs, c_in=cin, c_out=cout, k_vol=k, bytes=b, flops=f,
-                               algo=L.cw.algo))
+                               algo="fp16x3" if L.cw is None else L.cw.algo))
             tot_b += b
             tot_f += f
         return dict(layers=layers, bytes=tot_b, flops=tot_f, dense_bytes=int(self._state["dense"].numel() * 4))

@@ -238,6 +238,85 @@ int d3b_rulebook_dense2d(int32_t batch, int32_t height, int32_t width, const int
                          int32_t* n_rows, void* stream);
 
 /* ========================================================================= *
+ * 3b. Split-f16 ("FP16x3") convolutions: fp32-equivalent accuracy on the f16 tensor pipe, deterministic.
+ *
+ *     Activations are carried as TWO f16 planes of the same shape, hi = f16(x) and lo = f16(x - hi) (x = hi + lo
+ *     to 22 significant bits, |x| < 65504); weights are split the same way after an exact power-of-two scaling
+ *     2^w_exp (undone by `acc_scale` = 2^-w_exp in the epilogue).  The kernels compute hi.hi + hi.lo + lo.hi with
+ *     fp32 accumulation.  A result outside the f16 range cannot be carried: the kernels then OR 1 into `*overflow`
+ *     (device int, may be NULL) and the caller must fall back to the tf32 path -- nothing saturates silently.
+ *     Same reference call sites as section 3 (scn.py:106-157,323-355; necks/rpn.py:82-159; mg_head.py:198-230).
+ * ========================================================================= */
+typedef struct {
+  int32_t c_in, c_out, k_vol;
+  const void* in_hi;             /* f16 [rows, c_in] (c_in % 8 == 0)                                          */
+  const void* in_lo;
+  const float* in_f32;           /* first layer only: fp32 rows [rows, c_in <= 16] (then in_hi = in_lo = NULL)  */
+  const float* weight;           /* fp32 [k_vol, c_in, c_out]: used by the fp32-input first layer only          */
+  const void* weight_packed;     /* d3b_conv16_pack_weight image                                                */
+  float acc_scale;               /* 2^-w_exp (1 for the fp32-input layer)                                       */
+  const float* bias;             /* [c_out] or NULL                                                             */
+  const float* scale;            /* folded BatchNorm [c_out] or NULL (with shift)                               */
+  const float* shift;
+  const void* residual_hi;       /* f16 [rows, c_out] planes added before the ReLU, or NULL                     */
+  const void* residual_lo;
+  int32_t relu;
+  void* out_hi;                  /* f16 [rows, c_out] planes (both or neither)                                  */
+  void* out_lo;
+  float* out_f32;                /* optional fp32 copy of the result [rows, c_out]                              */
+  int32_t* overflow;             /* device flag, may be NULL                                                    */
+} d3b_conv16_params;
+
+/* Size in halves / fill of the f16 weight image: packed[k][kb][hi|lo][n][64 channels, 128B-swizzled].
+ * 0 if the shape is not built (c_out in {16,32,64,128}, c_in <= 512, k_vol <= 32). */
+size_t d3b_conv16_packed_weight_halves(int32_t c_in, int32_t c_out, int32_t k_vol);
+int d3b_conv16_pack_weight(const float* weight_dev, int32_t c_in, int32_t c_out, int32_t k_vol, int32_t w_exp,
+                           void* packed_dev, void* stream);
+
+/* Output-stationary sparse convolution over a rulebook (nbr / tile_mask as in d3b_sparse_conv): no atomics, fixed
+ * summation order -> bit-identical results run to run. */
+int d3b_sparse_conv16(const int32_t* nbr, const uint32_t* tile_mask, const int32_t* n_out, int32_t out_cap,
+                      const d3b_conv16_params* p, void* stream);
+
+/* fp32 <-> plane conversions (API boundaries) and the sparse -> dense NHWC scatter on planes
+ * (channel = c*D + z, as d3b_sparse_to_bev_rows; rows given as planes OR as fp32). */
+int d3b_split16(const float* x, int64_t n, void* hi, void* lo, int32_t* overflow, void* stream);
+int d3b_merge16(const void* hi, const void* lo, int64_t n, float* x, void* stream);
+int d3b_sparse_to_bev16(const void* in_hi, const void* in_lo, const float* in_f32, const int32_t* coors,
+                        const int32_t* n_rows, int32_t row_cap, int32_t channels, const int32_t spatial[3],
+                        int32_t batch, void* out_hi, void* out_lo, void* stream);
+
+/* Dense NHWC convolution on planes [batch, h_in, w_in, c_in] through TMA tensor maps: 3x3 (stride 1 or 2) or 1x1,
+ * zero padding `pad`, `groups` weight blocks of c_out (32/64/128) channels each in one launch:
+ *   group g -> channel block cg = g % cgroups, sub-pixel ug = g / cgroups, (uy, ux) = (ug / up, ug % up);
+ *   conv output pixel (y, x) of group g is written to pixel (y*up + uy, x*up + ux) of the output tensor
+ *   [batch, h_out*up, w_out*up, out_channels], channels [out_c0 + cg*c_out, out_c0 + (cg+1)*c_out).
+ * cgroups > 1 tiles a wide C_out; up > 1 (with ksize 1) is ConvTranspose2d(kernel = stride = up)
+ * (necks/rpn.py:108-122).  weight_packed = the groups' d3b_conv16_pack_weight images back to back;
+ * bias / scale / shift hold groups * c_out entries, group-major. */
+typedef struct {
+  int32_t batch, h_in, w_in, c_in;
+  int32_t c_out;                 /* per group */
+  int32_t ksize, stride, pad;
+  int32_t groups, cgroups, up;
+  const void* in_hi;
+  const void* in_lo;
+  const void* weight_packed;
+  float acc_scale;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int32_t relu;
+  int32_t out_channels, out_c0;
+  void* out_hi;
+  void* out_lo;
+  float* out_f32;
+  int32_t* overflow;
+} d3b_bev16_params;
+
+int d3b_bev_conv16(const d3b_bev16_params* p, void* stream);
+
+/* ========================================================================= *
  * 4. Rotated-box BEV IoU / NMS
  * ========================================================================= */
 #define D3B_BOX_XYXYR 0   /* [x1,y1,x2,y2,ry]: det3d/ops/iou3d/src/iou3d_kernel.cu:108-221 */
