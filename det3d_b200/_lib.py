@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdet3d_b200.so")
+LIB_PATH = os.environ.get("D3B_LIB") or os.path.join(_HERE, "lib", "libdet3d_b200.so")   # D3B_LIB: development builds
 
 D3B_OK = 0
 ALGO_SIMT = 0
@@ -136,6 +136,8 @@ SIGNATURES = {
     "d3b_feature_epilogue": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "d3b_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_pillar_features": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "d3b_voxelize_point_lists": (_vp, [C.POINTER(VoxelCfg), _i32, _i32, _vp]),
+    "d3b_pillar_features_lists": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "d3b_sparse_to_bev_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _I3, _i32, _vp, _vp]),
     "d3b_rulebook_dense2d": (C.c_int, [_i32, _i32, _i32, C.c_int32 * 2, C.c_int32 * 2, _vp, _vp, _vp, _vp]),
     "d3b_conv16_packed_weight_halves": (_sz, [_i32, _i32, _i32]),
@@ -218,6 +220,28 @@ def on_device_of(*tensors):
     else:
         with torch.cuda.device(dev):
             yield
+
+
+# bench.py hook: when set to a list, `timed(tag)` brackets the enclosed C-ABI calls with CUDA events recorded on the
+# launching (current) stream and appends (tag, start, end, info) -- per-stage kernel times for the roofline entries.
+PROFILE_EVENTS = None
+
+
+@contextlib.contextmanager
+def timed(tag, **info):
+    events = PROFILE_EVENTS
+    if events is None:
+        yield
+        return
+    import torch
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    try:
+        yield
+    finally:
+        ev1.record()
+        events.append((tag, ev0, ev1, info))
 
 
 def launch_count():

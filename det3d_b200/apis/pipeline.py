@@ -32,8 +32,12 @@ class InferencePipeline:
         # VoxelFeatureExtractorV3 only needs the per-voxel mean (fused into the voxelizer); the pillar reader
         # consumes the point slots themselves
         self._reader_takes_points = cfg.model["reader"]["type"] != "VoxelFeatureExtractorV3"
+        # a pillar reader that can walk the voxelizer's point-index lists does not need the [M, P, ndim] tensor either
+        self._reader_takes_lists = (self._reader_takes_points and hasattr(self.model.reader, "forward_lists")
+                                    and len(getattr(self.model.reader, "pfn_layers", [])) == 1)
         self.voxelizer = Voxelizer(vg["voxel_size"], vg["range"], vg["max_points_in_voxel"], vg["max_voxel_num"],
-                                   want_voxels=self._reader_takes_points, want_mean=not self._reader_takes_points)
+                                   want_voxels=self._reader_takes_points and not self._reader_takes_lists,
+                                   want_mean=not self._reader_takes_points)
         self.grid_size = self.voxelizer.grid_size
         self.num_point_features = int(cfg.model["reader"].get("num_input_features", 4))
         out_size_factor = cfg.assigner["out_size_factor"] if "assigner" in cfg else 8
@@ -61,6 +65,8 @@ class InferencePipeline:
             num_voxels=[None] * batch, shape=[self.grid_size], anchors=self.anchors(batch),
             n_voxels_dev=vox["counts"][batch:batch + 1],
         )
+        if self._reader_takes_lists:
+            example["point_lists"] = dict(vox["point_lists"], counts=vox["counts"])
         prev, prev_bench = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
         if self.strict_fp32:
             torch.backends.cudnn.allow_tf32 = False

@@ -98,5 +98,27 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_debug():
+    """Development library with soft wait time-outs (-DD3B_SOFT_TIMEOUT): lib/libdet3d_b200_dbg.so, selected at run
+    time with D3B_LIB=<path>.  Never loaded by default."""
+    os.makedirs(os.path.join(LIB_DIR, "obj_dbg"), exist_ok=True)
+    out = os.path.join(LIB_DIR, "libdet3d_b200_dbg.so")
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(LIB_DIR, "obj_dbg", os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-DD3B_SOFT_TIMEOUT", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        text, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, text.decode(errors="replace")))
+    subprocess.run([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", out] + objs, check=True)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

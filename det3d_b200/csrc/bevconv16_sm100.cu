@@ -145,7 +145,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
             for (int ky0 = 0; ky0 < KS; ky0 += Cfg::kRowsPerAStage) {
               // ---- A stage: {half 0, half 1} x {hi, lo} patches ----
               const int sa = a_it % kBvAStages;
-              mbar_wait(a_empty(sa), ((a_it / kBvAStages) & 1u) ^ 1u);
+              D3B_WAIT(a_empty(sa), ((a_it / kBvAStages) & 1u) ^ 1u, 1);
               mbar_arrive_expect_tx(a_full(sa), Cfg::kAStageBytes);
               const uint32_t dst = a_base + sa * Cfg::kAStageBytes;
               const int cy = STRIDE == 1 ? y0 - g.pad : y0 * STRIDE + ky0 - g.pad;
@@ -160,7 +160,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
               for (int r = 0; r < Cfg::kRowsPerAStage; ++r) {
                 const int ky = ky0 + r;
                 const int sb = b_it % Cfg::kBStages;
-                mbar_wait(b_empty(sb), ((b_it / Cfg::kBStages) & 1u) ^ 1u);
+                D3B_WAIT(b_empty(sb), ((b_it / Cfg::kBStages) & 1u) ^ 1u, 2);
                 mbar_arrive_expect_tx(b_full(sb), Cfg::kBBytes);
                 tma_bulk_g2s(b_base + sb * Cfg::kBBytes,
                              wgrp + ((size_t)(ky * KS + kx) * g.n_kb + kb) * (Cfg::kBBytes / 2), Cfg::kBBytes, b_full(sb));
@@ -177,7 +177,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
     constexpr uint32_t idesc1 = umma_idesc_f16(128, COUT);       // A_lo x B_hi
     uint32_t a_it = 0, b_it = 0, tile_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-      mbar_wait(acc_empty, (tile_it & 1u) ^ 1u);
+      D3B_WAIT(acc_empty, (tile_it & 1u) ^ 1u, 3);
       tc_fence_after();
       uint32_t accumulate = 0;
       for (int kb = 0; kb < g.n_kb; ++kb) {
@@ -185,10 +185,10 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         for (int kx = 0; kx < KS; ++kx) {
           for (int ky0 = 0; ky0 < KS; ky0 += Cfg::kRowsPerAStage) {
             const int sa = a_it % kBvAStages;
-            mbar_wait(a_full(sa), (a_it / kBvAStages) & 1u);
+            D3B_WAIT(a_full(sa), (a_it / kBvAStages) & 1u, 4);
             for (int r = 0; r < Cfg::kRowsPerAStage; ++r, ++b_it) {
               const int sb = b_it % Cfg::kBStages;
-              mbar_wait(b_full(sb), (b_it / Cfg::kBStages) & 1u);
+              D3B_WAIT(b_full(sb), (b_it / Cfg::kBStages) & 1u, 5);
               tc_fence_after();
               if (lane == 0) {
                 const uint32_t bt = b_base + sb * Cfg::kBBytes;
@@ -236,7 +236,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       const int oy = y * g.up + ug / g.up, ox = x * g.up + ug % g.up;
       const size_t row_off = (((size_t)b * g.out_h + oy) * g.out_w + ox) * (size_t)g.out_channels + g.out_c0 + cg * COUT;
       const int pcol = grp * COUT;              // per-group epilogue parameters are laid out group-major
-      mbar_wait(acc_full, tile_it & 1u);
+      D3B_WAIT(acc_full, tile_it & 1u, 6);
       tc_fence_after();
       const uint32_t t0 = tmem_d + half * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
@@ -418,3 +418,12 @@ extern "C" int d3b_bev_conv16(const d3b_bev16_params* p, void* stream_) {
   set_error("d3b_bev_conv16: C_out per group %d not in {32, 64, 128}", p->c_out);
   return D3B_ERR_UNSUPPORTED;
 }
+
+#ifdef D3B_SOFT_TIMEOUT
+extern "C" int d3b_debug_fault_bevconv16(unsigned int* host8) {
+  cudaError_t e = cudaMemcpyFromSymbol(host8, d3b::g_d3b_fault, 32);
+  unsigned int zeros[8] = {0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(d3b::g_d3b_fault, zeros, 32);
+  return (int)e;
+}
+#endif

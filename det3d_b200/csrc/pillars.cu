@@ -16,20 +16,64 @@ namespace {
 constexpr int kPillarWarps = 4;
 constexpr int kMaxUnitsPerLane = 4;   // units <= 128
 constexpr int kMaxIn = 16;            // ndim + 5 <= 16
+constexpr int kPillarMaxBatch = 64;
+constexpr int kListSentinel = 0x7f000000;   // voxelize.cu: list slots >= this are empty
+
+// Where a pillar's points come from: the materialised [rows, P, ndim] voxel buffer of the reference
+// (pillar_encoder.py:115-129 consumes exactly that), or -- fused with the voxelizer, SURVEY 8f.3 -- the voxelizer's
+// per-voxel point-index lists (csrc/voxelize.cu `lists`: [batch][max_voxels][P] indices into `points`), in which case
+// the [rows, P, ndim] tensor never exists.
+struct PillarSrc {
+  const float* voxels;        // dense mode
+  const float* points;        // list mode: [n_total, ndim]
+  const int* lists;           // list mode
+  const int* counts;          // list mode: voxels per cloud [batch]
+  int batch, max_voxels;
+};
+
+// stage the `cnt` points of output row `row` into `my` (one warp)
+template <int NDIM_T>
+__device__ __forceinline__ void stage_points(const PillarSrc& src, const int* pref, int row, int cnt, int P, int ndim_rt,
+                                             int lane, float* my) {
+  const int ndim = NDIM_T > 0 ? NDIM_T : ndim_rt;
+  if (src.lists == nullptr) {
+    const float* s = src.voxels + (size_t)row * P * ndim;
+    for (int i = lane; i < cnt * ndim; i += 32) my[i] = s[i];
+    return;
+  }
+  int b = 0;
+  while (b + 1 < src.batch && row >= pref[b + 1]) ++b;
+  const int* L = src.lists + ((size_t)b * src.max_voxels + (row - pref[b])) * P;
+  for (int p = lane; p < cnt; p += 32) {
+    const int idx = L[p];
+    const float* q = src.points + (size_t)idx * ndim;
+    if (NDIM_T == 4) {
+      *reinterpret_cast<float4*>(my + p * 4) = idx < kListSentinel ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int d = 0; d < ndim; ++d) my[p * ndim + d] = idx < kListSentinel ? __ldg(q + d) : 0.f;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kPillarWarps * 32)
-pillar_features_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points,
+pillar_features_kernel(const PillarSrc src, const int* __restrict__ num_points,
                        const int* __restrict__ coors, const int* __restrict__ n_rows, int row_cap, int P,
                        int ndim, int units, const float* __restrict__ weight, const float* __restrict__ scale,
                        const float* __restrict__ shift, float vx, float vy, float x_offset, float y_offset,
                        float* __restrict__ out) {
   extern __shared__ float smem[];
+  __shared__ int pref[kPillarMaxBatch + 1];
   const int n_in = ndim + 5;
   float* wt = smem;                                   // [n_in][units]  (transposed: lanes read consecutive floats)
   float* pts = smem + n_in * units;                   // [kPillarWarps][P * ndim]
   for (int i = threadIdx.x; i < n_in * units; i += blockDim.x) {
     const int c = i / n_in, f = i - c * n_in;         // weight is [units][n_in] (nn.Linear layout)
     wt[f * units + c] = weight[i];
+  }
+  if (threadIdx.x == 0 && src.lists != nullptr) {
+    int acc = 0;
+    for (int b = 0; b < src.batch; ++b) { pref[b] = acc; acc += src.counts[b]; }
+    pref[src.batch] = acc;
   }
   __syncthreads();
 
@@ -52,10 +96,8 @@ pillar_features_kernel(const float* __restrict__ voxels, const int* __restrict__
       continue;
     }
     const int cnt = min(max(num_points[row], 1), P);
-    const float* src = voxels + (size_t)row * P * ndim;
-    const int live = cnt * ndim;
     __syncwarp();
-    for (int i = lane; i < live; i += 32) my[i] = src[i];
+    stage_points<0>(src, pref, row, cnt, P, ndim, lane, my);
     __syncwarp();
 
     // per-pillar mean of xyz over the occupied slots (padding slots hold zeros in the reference's buffer, so
@@ -110,18 +152,24 @@ pillar_features_kernel(const float* __restrict__ voxels, const int* __restrict__
 // ndim is a template parameter for the two point layouts the configs use so that f[] stays in registers
 template <int NDIM>
 __global__ void __launch_bounds__(kPillarWarps * 32)
-pillar_features_fixed(const float* __restrict__ voxels, const int* __restrict__ num_points,
+pillar_features_fixed(const PillarSrc src, const int* __restrict__ num_points,
                       const int* __restrict__ coors, const int* __restrict__ n_rows, int row_cap, int P,
                       const float* __restrict__ weight, const float* __restrict__ scale,
                       const float* __restrict__ shift, float vx, float vy, float x_offset, float y_offset,
                       float* __restrict__ out) {
   constexpr int kIn = NDIM + 5, kUnits = 64;
   extern __shared__ float smem[];
+  __shared__ int pref[kPillarMaxBatch + 1];
   float* wt = smem;                                   // [kIn][64]
   float* pts = smem + kIn * kUnits;
   for (int i = threadIdx.x; i < kIn * kUnits; i += blockDim.x) {
     const int c = i / kIn, f = i - c * kIn;
     wt[f * kUnits + c] = weight[i];
+  }
+  if (threadIdx.x == 0 && src.lists != nullptr) {
+    int acc = 0;
+    for (int b = 0; b < src.batch; ++b) { pref[b] = acc; acc += src.counts[b]; }
+    pref[src.batch] = acc;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,10 +188,8 @@ pillar_features_fixed(const float* __restrict__ voxels, const int* __restrict__ 
     }
     const int raw = num_points[row];
     const int cnt = min(max(raw, 1), P);
-    const float* src = voxels + (size_t)row * P * NDIM;
-    const int live = cnt * NDIM;
     __syncwarp();
-    for (int i = lane; i < live; i += 32) my[i] = src[i];
+    stage_points<NDIM>(src, pref, row, cnt, P, NDIM, lane, my);
     __syncwarp();
     float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int p = lane; p < cnt; p += 32) {
@@ -189,13 +235,11 @@ pillar_features_fixed(const float* __restrict__ voxels, const int* __restrict__ 
 
 using namespace d3b;
 
-extern "C" int d3b_pillar_features(const float* voxels, const int32_t* num_points, const int32_t* coors,
-                                   const int32_t* n_rows, int32_t row_cap, int32_t max_points, int32_t ndim,
-                                   int32_t units, const float* weight, const float* scale, const float* shift,
-                                   float vx, float vy, float x_offset, float y_offset, float* out,
-                                   void* stream_) {
-  D3B_REQUIRE(voxels && num_points && coors && n_rows && weight && scale && shift && out,
-              "pillar_features: null pointer");
+static int launch_pillars(const PillarSrc& src, const int32_t* num_points, const int32_t* coors, const int32_t* n_rows,
+                          int32_t row_cap, int32_t max_points, int32_t ndim, int32_t units, const float* weight,
+                          const float* scale, const float* shift, float vx, float vy, float x_offset, float y_offset,
+                          float* out, void* stream_) {
+  D3B_REQUIRE(num_points && coors && n_rows && weight && scale && shift && out, "pillar_features: null pointer");
   D3B_REQUIRE(row_cap >= 0 && max_points >= 1, "pillar_features: bad sizes (rows %d, points %d)", row_cap, max_points);
   if (ndim < 3 || ndim + 5 > kMaxIn || units < 32 || units > 32 * kMaxUnitsPerLane || (units & 31)) {
     set_error("pillar_features: ndim %d / units %d not built (3 <= ndim <= %d, units in {32,64,96,128})", ndim,
@@ -212,7 +256,7 @@ extern "C" int d3b_pillar_features(const float* voxels, const int32_t* num_point
     if (smem > 48 * 1024)                                                                                      \
       D3B_CUDA(cudaFuncSetAttribute(pillar_features_fixed<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     pillar_features_fixed<ND><<<grid, kPillarWarps * 32, smem, stream>>>(                                      \
-        voxels, num_points, coors, n_rows, row_cap, max_points, weight, scale, shift, vx, vy, x_offset,        \
+        src, num_points, coors, n_rows, row_cap, max_points, weight, scale, shift, vx, vy, x_offset,           \
         y_offset, out);                                                                                        \
   }
   if (units == 64 && ndim == 4) D3B_PILLAR_FIXED(4)
@@ -221,10 +265,36 @@ extern "C" int d3b_pillar_features(const float* voxels, const int32_t* num_point
     if (smem > 48 * 1024)
       D3B_CUDA(cudaFuncSetAttribute(pillar_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pillar_features_kernel<<<grid, kPillarWarps * 32, smem, stream>>>(
-        voxels, num_points, coors, n_rows, row_cap, max_points, ndim, units, weight, scale, shift, vx, vy,
+        src, num_points, coors, n_rows, row_cap, max_points, ndim, units, weight, scale, shift, vx, vy,
         x_offset, y_offset, out);
   }
 #undef D3B_PILLAR_FIXED
   D3B_LAUNCH_CHECK();
   return D3B_OK;
+}
+
+extern "C" int d3b_pillar_features(const float* voxels, const int32_t* num_points, const int32_t* coors,
+                                   const int32_t* n_rows, int32_t row_cap, int32_t max_points, int32_t ndim,
+                                   int32_t units, const float* weight, const float* scale, const float* shift,
+                                   float vx, float vy, float x_offset, float y_offset, float* out,
+                                   void* stream_) {
+  D3B_REQUIRE(voxels, "pillar_features: null voxels");
+  PillarSrc src;
+  src.voxels = voxels; src.points = nullptr; src.lists = nullptr; src.counts = nullptr; src.batch = 0; src.max_voxels = 0;
+  return launch_pillars(src, num_points, coors, n_rows, row_cap, max_points, ndim, units, weight, scale, shift, vx, vy,
+                        x_offset, y_offset, out, stream_);
+}
+
+extern "C" int d3b_pillar_features_lists(const float* points, const int32_t* lists, const int32_t* voxel_counts,
+                                         int32_t batch, int32_t max_voxels, const int32_t* num_points,
+                                         const int32_t* coors, const int32_t* n_rows, int32_t row_cap, int32_t max_points,
+                                         int32_t ndim, int32_t units, const float* weight, const float* scale,
+                                         const float* shift, float vx, float vy, float x_offset, float y_offset,
+                                         float* out, void* stream_) {
+  D3B_REQUIRE(points && lists && voxel_counts, "pillar_features_lists: null pointer");
+  D3B_REQUIRE(batch >= 1 && batch <= kPillarMaxBatch && max_voxels >= 1, "pillar_features_lists: batch %d / max_voxels %d", batch, max_voxels);
+  PillarSrc src;
+  src.voxels = nullptr; src.points = points; src.lists = lists; src.counts = voxel_counts; src.batch = batch; src.max_voxels = max_voxels;
+  return launch_pillars(src, num_points, coors, n_rows, row_cap, max_points, ndim, units, weight, scale, shift, vx, vy,
+                        x_offset, y_offset, out, stream_);
 }

@@ -24,8 +24,9 @@
 // the first half of the columns; the epilogue adds the two halves.  |x| >= 65504 cannot be represented: the epilogue
 // raises a device flag instead of silently saturating (the host checks it with the detections).
 //
-// Roles (672 threads): 4 gather groups x 4 warps (slot j -> group j % 4), 1 MMA warp (also owns TMEM), 4 epilogue
-// warps; two TMEM accumulators so the drain of tile t overlaps the MMAs of tile t+1; persistent grid <= 148 CTAs.
+// Roles: one gather group of 4 warps per pipeline stage (slot j -> group j % stages; 4 stages, 3 at C_out = 128), 1 MMA
+// warp (also owns TMEM), 4 epilogue warps; two TMEM accumulators so the drain of tile t overlaps the MMAs of tile t+1;
+// persistent grid <= 148 CTAs.
 // Algorithmic bytes per layer: N_in*C_in*4 + N_out*C_out*4 + P*8 + K*C_in*C_out*4.
 #include "umma.cuh"
 
@@ -33,10 +34,6 @@ namespace d3b {
 
 constexpr int kOsTileM = 128;
 constexpr int kOsKc = 64;                                  // channels per stage = one 128-byte swizzle row of f16
-constexpr int kOsGroups = 4;
-constexpr int kOsMmaWarp = 4 * kOsGroups;                  // warp 16
-constexpr int kOsEpiWarp0 = kOsMmaWarp + 1;                // warps 17..20 (warp & 3 = 1,2,3,0: one per TMEM quadrant)
-constexpr int kOsThreads = 32 * (kOsEpiWarp0 + 4);         // 672
 constexpr int kOsABytes = kOsTileM * 128;                  // one A plane tile (hi or lo)
 
 template <int COUT>
@@ -44,6 +41,14 @@ struct OsCfg {
   static constexpr int kBBytes = 2 * COUT * 128;           // [B_hi rows | B_lo rows]
   static constexpr int kStageBytes = 2 * kOsABytes + kBBytes;
   static constexpr int kStages = COUT >= 128 ? 3 : 4;
+  // One gather group per pipeline stage: group g only ever fills stage g.  (A group waits for "stage free" on the
+  // PARITY of the stage's empty barrier; that is unambiguous only if the group itself has seen the previous use of
+  // the stage go by -- with more groups than stages a group would meet a stage it last touched two uses ago, read a
+  // stale parity as "free" and overwrite live operands.)
+  static constexpr int kGroups = kStages;
+  static constexpr int kMmaWarp = 4 * kGroups;             // TMEM alloc + MMA issue
+  static constexpr int kEpiWarp0 = kMmaWarp + 1;           // four epilogue warps, warp & 3 = its TMEM lane quadrant
+  static constexpr int kThreads = 32 * (kEpiWarp0 + 4);    // 544 (3 groups) / 672 (4 groups)
   static constexpr int kAccCols = 2 * COUT;                // [hi.hi + lo.hi | hi.lo]
   static constexpr int kTmemCols = 2 * kAccCols;           // double-buffered across tiles (64 .. 512, a power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 32 * kOsTileM * 4;
@@ -131,7 +136,7 @@ __device__ __forceinline__ bool epilogue16(float (&v)[16], const OsEpi& e, size_
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(kOsThreads, 1)
+__global__ void __launch_bounds__(OsCfg<COUT>::kThreads, 1)
 spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, const int* __restrict__ nbr,
                    const unsigned int* __restrict__ tile_mask, const int* __restrict__ n_out_p, int out_cap, int c_in,
                    int n_kb, const __half* __restrict__ packed, OsEpi epi, __half* __restrict__ out_hi,
@@ -164,7 +169,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kOsMmaWarp) {
+  if (warp == Cfg::kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -178,7 +183,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
   uint32_t tile_it = 0;   // accumulator phase counter
 
-  if (warp < kOsMmaWarp) {
+  if (warp < Cfg::kMmaWarp) {
     // ===================== gather producers =====================
     const int group = warp >> 2, wq = warp & 3;
     const int g = lane >> 3, c = lane & 7;
@@ -192,8 +197,8 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const int n_slots = n_off * n_kb;
 
       // stage nbr[k][row0 .. row0+127] for the active offsets (one global round trip per tile)
-      asm volatile("bar.sync 1, %0;" ::"r"(128 * kOsGroups) : "memory");   // previous tile's readers are done
-      for (int idx = ptid; idx < n_off * kOsTileM; idx += 128 * kOsGroups) {
+      asm volatile("bar.sync 1, %0;" ::"r"(128 * Cfg::kGroups) : "memory");   // previous tile's readers are done
+      for (int idx = ptid; idx < n_off * kOsTileM; idx += 128 * Cfg::kGroups) {
         const int n = idx >> 7, r = idx & 127;
         unsigned int m = mask;
         for (int t = n; t > 0; --t) m &= m - 1;
@@ -201,15 +206,15 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         if (r == 0) koff_s[n] = k;
         nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)k * out_cap + row0 + r) : -1;
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(128 * kOsGroups) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(128 * Cfg::kGroups) : "memory");
 
-      for (int j = (int)((group + kOsGroups - (it0 % kOsGroups)) % kOsGroups); j < n_slots; j += kOsGroups) {
+      for (int j = (int)((group + Cfg::kGroups - (it0 % Cfg::kGroups)) % Cfg::kGroups); j < n_slots; j += Cfg::kGroups) {
         const int n = j / n_kb, kb = j - n * n_kb;
         const int ch = kb * kOsKc + c * 8;                 // this thread's 8 channels (16 bytes)
         const uint32_t it = it0 + (uint32_t)j;
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        D3B_WAIT(empty_bar(s), ph ^ 1u, 1);
         const uint32_t stage = smem_base + s * Cfg::kStageBytes;
         if (issues_tma) {
           mbar_arrive_expect_tx(full_bar(s), Cfg::kBBytes);
@@ -234,7 +239,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       }
       it0 += (uint32_t)n_slots;
     }
-  } else if (warp == kOsMmaWarp) {
+  } else if (warp == Cfg::kMmaWarp) {
     // ===================== MMA issuer (one elected lane) =====================
     constexpr uint32_t idesc2 = umma_idesc_f16(kOsTileM, 2 * COUT);   // A_hi x [B_hi | B_lo]
     constexpr uint32_t idesc1 = umma_idesc_f16(kOsTileM, COUT);       // A_lo x B_hi
@@ -244,7 +249,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       if (mask == 0) continue;
       const int n_slots = __popc(mask) * n_kb;
       const uint32_t buf = tile_it & 1u;
-      mbar_wait(acc_empty(buf), ((tile_it >> 1) & 1u) ^ 1u);
+      D3B_WAIT(acc_empty(buf), ((tile_it >> 1) & 1u) ^ 1u, 2);
       tc_fence_after();
       const uint32_t d_addr = tmem_d + buf * Cfg::kAccCols;
       uint32_t accumulate = 0;
@@ -253,7 +258,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         const uint32_t ph = (it / Cfg::kStages) & 1u;
         const int kb = j % n_kb;
         const int n_ks = min(kOsKc / 16, (c_in - kb * kOsKc + 15) / 16);
-        mbar_wait(full_bar(s), ph);
+        D3B_WAIT(full_bar(s), ph, 3);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
@@ -283,7 +288,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const int o = tile * kOsTileM + quad * 32 + lane;
       const uint32_t buf = tile_it & 1u;
       if (any) {
-        mbar_wait(acc_full(buf), (tile_it >> 1) & 1u);
+        D3B_WAIT(acc_full(buf), (tile_it >> 1) & 1u, 4);
         tc_fence_after();
       }
       const uint32_t t0 = tmem_d + buf * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
@@ -314,7 +319,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kOsMmaWarp) {
+  if (warp == Cfg::kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -452,7 +457,7 @@ static int launch_os16(const d3b_conv16_params* p, const int32_t* nbr, const uin
   const int n_tiles = div_up(out_cap, kOsTileM);
   const int grid = n_tiles < kNumSMs ? (n_tiles > 0 ? n_tiles : 1) : kNumSMs;
   const int n_kb = (p->c_in + kOsKc - 1) / kOsKc;
-  spconv_os16_kernel<COUT><<<grid, kOsThreads, Cfg::kSmemBytes, stream>>>(
+  spconv_os16_kernel<COUT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
       (const __half*)p->in_hi, (const __half*)p->in_lo, nbr, tile_mask, n_out, out_cap, p->c_in, n_kb,
       (const __half*)p->weight_packed, epi_of(p), (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, p->overflow);
   D3B_LAUNCH_CHECK();
@@ -568,3 +573,12 @@ extern "C" int d3b_sparse_to_bev16(const void* in_hi, const void* in_lo, const f
   D3B_LAUNCH_CHECK();
   return D3B_OK;
 }
+
+#ifdef D3B_SOFT_TIMEOUT
+extern "C" int d3b_debug_fault_spconv16(unsigned int* host8) {
+  cudaError_t e = cudaMemcpyFromSymbol(host8, d3b::g_d3b_fault, 32);
+  unsigned int zeros[8] = {0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(d3b::g_d3b_fault, zeros, 32);
+  return (int)e;
+}
+#endif

@@ -39,6 +39,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 28)) __trap();
   }
 }
+// Development aid (-DD3B_SOFT_TIMEOUT, never in the product library): a wait that times out records `code` in the
+// translation unit's fault word and RETURNS, so the kernel runs to its end and the host can read which wait starved.
+#ifdef D3B_SOFT_TIMEOUT
+static __device__ unsigned int g_d3b_fault[8];
+__device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, unsigned int code) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 20)) {
+      const unsigned int slot = atomicAdd(&g_d3b_fault[0], 1u);
+      if (slot < 7u) g_d3b_fault[1 + slot] = (code << 16) | (blockIdx.x & 0xffffu);
+      return;
+    }
+  }
+}
+#define D3B_WAIT(bar, parity, code) mbar_wait_dbg(bar, parity, code)
+#else
+#define D3B_WAIT(bar, parity, code) mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)

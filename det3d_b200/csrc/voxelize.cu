@@ -242,7 +242,8 @@ vox_emit(const VoxParams p, const float* __restrict__ points,
     if (blockIdx.x == 0) counts[p.batch] = s;
   }
   __syncthreads();
-  const int per_voxel = p.max_points * p.ndim;
+  // without the [M, max_points, ndim] output only slot 0's threads have work (mean / coors / counts): shrink the index space
+  const int per_voxel = (voxels != nullptr ? p.max_points : 1) * p.ndim;
   const long long total = (long long)pref[p.batch] * per_voxel;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -327,6 +328,12 @@ extern "C" size_t d3b_voxelize_workspace_bytes(const d3b_voxel_cfg* cfg, int32_t
   return carve(cfg, n_points_total, batch, nullptr).bytes;
 }
 
+extern "C" const int32_t* d3b_voxelize_point_lists(const d3b_voxel_cfg* cfg, int32_t n_points_total, int32_t batch,
+                                                   void* workspace) {
+  if (!cfg || batch < 1 || n_points_total < 0 || !workspace) return nullptr;
+  return carve(cfg, n_points_total, batch, (char*)workspace).lists;
+}
+
 extern "C" int d3b_voxelize(const d3b_voxel_cfg* cfg, const float* points,
                             const int32_t* cloud_offsets, int32_t batch, float* voxels,
                             int32_t* coors, int32_t* num_points, float* mean_feats,
@@ -381,7 +388,7 @@ extern "C" int d3b_voxelize(const d3b_voxel_cfg* cfg, const float* points,
     vox_lists<<<grid_for(n_total, 256), 256, 0, stream>>>(p, w.pslot, w.vid, w.cut, w.lists);
     D3B_LAUNCH_CHECK();
   }
-  const long long cap_elems = (long long)batch * cfg->max_voxels * cfg->max_points * cfg->ndim;
+  const long long cap_elems = (long long)batch * cfg->max_voxels * (voxels != nullptr ? cfg->max_points : 1) * cfg->ndim;
   vox_emit<<<grid_for(cap_elems, 256), 256, 0, stream>>>(p, points, w.keys, w.vslot, w.lists,
                                                           voxel_counts, voxels, coors, num_points,
                                                           mean_feats);

@@ -271,7 +271,7 @@ class MultiGroupHead(nn.Module):
             ws = bufs["ws"].get(task_id)
             if ws is None or ws.numel() < need:
                 ws = bufs["ws"][task_id] = torch.empty(need, dtype=torch.uint8, device=dev)
-            with _lib.on_device_of(packed, first):
+            with _lib.on_device_of(packed, first), _lib.timed("predict", anchors=int(anchors.shape[0]), batch=B, pre=pre, post=post):
                 st = _lib.lib().d3b_predict_task(C.byref(q), packed.data_ptr(), D, row_offset, None, ws.data_ptr(),
                                                 ws.numel(), _lib.current_stream())
             _lib.check(st, "d3b_predict_task")

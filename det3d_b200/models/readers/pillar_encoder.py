@@ -90,7 +90,7 @@ class PillarFeatureNet(nn.Module):
         out = torch.empty((m, layer.units), dtype=torch.float32, device=features.device)
         if n_dev is None:
             n_dev = torch.tensor([m], dtype=torch.int32, device=features.device)
-        with _lib.on_device_of(features, num_voxels, coors, n_dev):
+        with _lib.on_device_of(features, num_voxels, coors, n_dev), _lib.timed("pillar_features", rows=m, points=p, ndim=ndim):
             st = _lib.lib().d3b_pillar_features(
                 features.contiguous().data_ptr(), num_voxels.to(torch.int32).contiguous().data_ptr(),
                 coors.to(torch.int32).contiguous().data_ptr(), n_dev.data_ptr(), m, p, ndim, layer.units, w.data_ptr(),
@@ -98,6 +98,39 @@ class PillarFeatureNet(nn.Module):
                 C.c_float(self.y_offset), out.data_ptr(), _lib.current_stream())
         _lib.check(st, "d3b_pillar_features")
         return out[:m]
+
+    def forward_lists(self, point_lists, num_voxels, coors, row_cap, n_dev):
+        """The reader fused with the voxelizer: points are fetched through the voxelizer's per-voxel index
+        lists (`Voxelizer(...)(...)["point_lists"]`), the [M, P, ndim] voxel tensor is never materialised.
+        num_voxels [cap] i32, coors [cap, 4] i32 and n_dev (device row count) come from the same voxelizer call."""
+        layer = self.pfn_layers[0]
+        assert not self.training and len(self.pfn_layers) == 1 and not self._with_distance
+        bn = layer.norm
+        key = (bn.running_var._version, bn.running_mean._version, bn.weight._version, bn.bias._version,
+               layer.linear.weight._version, bn.running_var.data_ptr(), layer.linear.weight.data_ptr())
+        cache = self.__dict__.get("_folded")
+        if cache is None or cache[0] != key:
+            var = bn.running_var.double()
+            scale = (bn.weight.double() / torch.sqrt(var + bn.eps)).float().contiguous()
+            shift = (bn.bias.double() - bn.running_mean.double() * bn.weight.double() / torch.sqrt(var + bn.eps)).float().contiguous()
+            cache = self.__dict__["_folded"] = (key, scale, shift, layer.linear.weight.detach().float().contiguous())
+        _k, scale, shift, w = cache
+        points = point_lists["points"]
+        ndim = points.shape[1]
+        okey = (row_cap, points.device)
+        outs = self.__dict__.setdefault("_out_bufs", {})
+        out = outs.get(okey)
+        if out is None:
+            out = outs[okey] = torch.empty((max(row_cap, 1), layer.units), dtype=torch.float32, device=points.device)
+        with _lib.on_device_of(points, num_voxels, coors, n_dev), _lib.timed("pillar_features", rows=row_cap, points=point_lists["max_points"], ndim=ndim, fused=True):
+            st = _lib.lib().d3b_pillar_features_lists(
+                points.data_ptr(), point_lists["lists_ptr"], point_lists["counts"].data_ptr(), point_lists["batch"],
+                point_lists["max_voxels"], num_voxels.data_ptr(), coors.data_ptr(), n_dev.data_ptr(), row_cap,
+                point_lists["max_points"], ndim, layer.units, w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                C.c_float(self.vx), C.c_float(self.vy), C.c_float(self.x_offset), C.c_float(self.y_offset), out.data_ptr(),
+                _lib.current_stream())
+        _lib.check(st, "d3b_pillar_features_lists")
+        return out
 
     def forward(self, features, num_voxels, coors, n_dev=None):
         if self._fusable(features):

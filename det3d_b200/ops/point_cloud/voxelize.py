@@ -82,11 +82,17 @@ class Voxelizer:
         batch = len(offsets) - 1
         b = self._buffers(n_total, batch, ndim, points.device)
         off = (C.c_int32 * (batch + 1))(*[int(o) for o in offsets])
-        with _lib.on_device_of(points):
+        with _lib.on_device_of(points), _lib.timed("voxelize", n_points=n_total, ndim=ndim, batch=batch):
             st = _lib.lib().d3b_voxelize(
                 C.byref(b["cfg"]), points.data_ptr() if n_total > 0 else None, off, batch,
                 _lib.ptr(b["voxels"]), b["coors"].data_ptr(), b["num_points"].data_ptr(), _lib.ptr(b["mean"]),
                 b["counts"].data_ptr(), b["ws"].data_ptr(), b["ws"].numel(), _lib.current_stream(),
             )
         _lib.check(st, "d3b_voxelize")
-        return {k: b[k] for k in ("voxels", "coors", "num_points", "mean", "counts")}
+        out = {k: b[k] for k in ("voxels", "coors", "num_points", "mean", "counts")}
+        # the per-voxel point-index lists the voxelizer built on the way ([batch][max_voxels][max_points] indices into
+        # `points`, valid until the next call): what the fused pillar reader consumes instead of `voxels`
+        out["point_lists"] = dict(points=points, lists_ptr=_lib.lib().d3b_voxelize_point_lists(
+            C.byref(b["cfg"]), n_total, batch, b["ws"].data_ptr()), batch=batch, max_voxels=self.max_voxels,
+            max_points=self.max_num_points, keepalive=b["ws"])
+        return out

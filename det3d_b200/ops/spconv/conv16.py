@@ -16,9 +16,6 @@ import torch
 from ... import _lib
 from ..._lib import Bev16Params, Conv16Params
 
-# bench.py hook: when set to a list, every conv16 launch is bracketed by CUDA events recorded on the launching
-# stream and (tag, start, end) is appended here.
-PROFILE_EVENTS = None
 
 
 class Planes:
@@ -146,17 +143,10 @@ def sparse_conv16(x, rb, cw, out, residual=None, out_f32=None, overflow=None, ta
         assert out_f32.dtype == torch.float32 and out_f32.is_contiguous() and out_f32.shape[1] == cw.c_out
         p.out_f32 = out_f32.data_ptr()
     p.overflow = _lib.ptr(overflow)
-    events = PROFILE_EVENTS
-    if events is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    with _lib.on_device_of(dev_t):
+    with _lib.on_device_of(dev_t), _lib.timed(tag, c_in=cw.c_in, c_out=cw.c_out, k_vol=cw.k_vol, math="fp16x3"):
         st = _lib.lib().d3b_sparse_conv16(rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), rb.out_level.n.data_ptr(),
                                           rb.out_level.cap, C.byref(p), _lib.current_stream())
     _lib.check(st, "d3b_sparse_conv16")
-    if events is not None:
-        ev1.record()
-        events.append((tag, ev0, ev1))
     return out
 
 
@@ -252,16 +242,11 @@ class BevConv16:
                 assert tuple(out_f32.shape) == tuple(out.shape)
             p.out_f32 = out_f32.data_ptr()
         p.overflow = _lib.ptr(overflow)
-        events = PROFILE_EVENTS
-        if events is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        with _lib.on_device_of(x.buf):
+        with _lib.on_device_of(x.buf), _lib.timed(tag, flops=self.flops(b, h, w), c_in=self.c_in, c_out=self.c_out_total,
+                                                  ksize=self.ksize, stride=self.stride, up=self.up, math="fp16x3",
+                                                  pixels_in=b * h * w, pixels_out=b * ho * wo):
             st = _lib.lib().d3b_bev_conv16(C.byref(p), _lib.current_stream())
         _lib.check(st, "d3b_bev_conv16")
-        if events is not None:
-            ev1.record()
-            events.append((tag, ev0, ev1))
         return out if out is not None else out_f32
 
     def flops(self, b, h, w):

@@ -19,9 +19,6 @@ from ... import _lib
 from ..._lib import ConvParams, SiteIndex
 
 TILE_M = 128
-# bench.py hook: when set to a list, every sparse_conv launch is bracketed by CUDA events
-# recorded on the launching stream and the (start, end) pair is appended here.
-PROFILE_EVENTS = None
 
 
 def _i3(v):
@@ -84,9 +81,10 @@ class SparseLevel:
     def rebuild_index(self):
         """Re-run the hash insert for new coordinates in the same buffers."""
         assert self.index is not None and self.index.hash_keys
-        st = _lib.lib().d3b_index_build_hash(
-            self.coors.data_ptr(), self.n.data_ptr(), self.cap, C.byref(self.index), _lib.current_stream()
-        )
+        with _lib.timed("rulebook", kind="hash"):
+            st = _lib.lib().d3b_index_build_hash(
+                self.coors.data_ptr(), self.n.data_ptr(), self.cap, C.byref(self.index), _lib.current_stream()
+            )
         _lib.check(st, "d3b_index_build_hash")
 
     # -- strided-level index: bitmap ------------------------------------------
@@ -176,10 +174,11 @@ def _pair_ptrs(rb, with_pairs):
 def build_subm_rulebook(rb, with_pairs=False):
     level = rb.out_level
     pin, pout, pcnt = _pair_ptrs(rb, with_pairs)
-    st = _lib.lib().d3b_rulebook_subm(
-        level.coors.data_ptr(), level.n.data_ptr(), level.cap, C.byref(level.index), _i3(rb.ksize),
-        rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), pin, pout, pcnt, _lib.current_stream(),
-    )
+    with _lib.timed("rulebook", kind="subm", k_vol=rb.k_vol):
+        st = _lib.lib().d3b_rulebook_subm(
+            level.coors.data_ptr(), level.n.data_ptr(), level.cap, C.byref(level.index), _i3(rb.ksize),
+            rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), pin, pout, pcnt, _lib.current_stream(),
+        )
     _lib.check(st, "d3b_rulebook_subm")
     return rb
 
@@ -207,12 +206,13 @@ def alloc_conv_rulebook(in_level, ksize, stride, padding, out_cap=None):
 def build_conv_rulebook(rb, with_pairs=False):
     i, o = rb.in_level, rb.out_level
     pin, pout, pcnt = _pair_ptrs(rb, with_pairs)
-    st = _lib.lib().d3b_rulebook_conv(
-        i.coors.data_ptr(), i.n.data_ptr(), i.cap, C.byref(i.index), _i3(rb.ksize), _i3(rb.stride),
-        _i3(rb.padding), C.byref(o.index), o.coors.data_ptr(), o.n.data_ptr(), o.cap,
-        rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), pin, pout, pcnt, rb._ws.data_ptr(), rb._ws.numel(),
-        _lib.current_stream(),
-    )
+    with _lib.timed("rulebook", kind="conv", k_vol=rb.k_vol):
+        st = _lib.lib().d3b_rulebook_conv(
+            i.coors.data_ptr(), i.n.data_ptr(), i.cap, C.byref(i.index), _i3(rb.ksize), _i3(rb.stride),
+            _i3(rb.padding), C.byref(o.index), o.coors.data_ptr(), o.n.data_ptr(), o.cap,
+            rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), pin, pout, pcnt, rb._ws.data_ptr(), rb._ws.numel(),
+            _lib.current_stream(),
+        )
     _lib.check(st, "d3b_rulebook_conv")
     return rb
 
@@ -313,18 +313,14 @@ def sparse_conv(feat_in, rb, cw, feat_out, residual=None, in_act=None, out_zeroe
             p.in_bias, p.in_scale, p.in_shift, p.in_relu = _lib.ptr(b), _lib.ptr(sc), _lib.ptr(sh), 1 if relu else 0
     else:
         assert in_act is None, "only the pair-based kernel applies a deferred input activation"
-    events = PROFILE_EVENTS
-    if events is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    st = _lib.lib().d3b_sparse_conv(
-        feat_in.data_ptr(), rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), rb.out_level.n.data_ptr(),
-        rb.out_level.cap, C.byref(p), feat_out.data_ptr(), _lib.current_stream(),
-    )
+    dense = rb.kind == "dense2d"
+    tag = ("bev3x3" if rb.k_vol == 9 else "bev1x1") if dense else "sparse"
+    with _lib.timed(tag, c_in=cw.c_in, c_out=cw.c_out, k_vol=cw.k_vol, math="tf32x3"):
+        st = _lib.lib().d3b_sparse_conv(
+            feat_in.data_ptr(), rb.nbr.data_ptr(), rb.tile_mask.data_ptr(), rb.out_level.n.data_ptr(),
+            rb.out_level.cap, C.byref(p), feat_out.data_ptr(), _lib.current_stream(),
+        )
     _lib.check(st, "d3b_sparse_conv")
-    if events is not None:
-        ev1.record()
-        events.append((ev0, ev1))
     return feat_out
 
 

@@ -126,3 +126,82 @@ def demo_weights_(model, seed=0, cls_scale=0.005, cls_bias=-1.05, box_scale=0.00
             task.conv_box.weight.mul_(box_scale)
             task.conv_box.bias.zero_()
     return model
+
+
+def calibrate_demo_weights_(model, cfg, clouds, seed=0, pass_fraction=0.03, box_std=0.1):
+    """Data-driven finish of `demo_weights_` (GPU): makes the random-weight network behave like a trained one --
+    every BatchNorm's running statistics are set from the activations it actually sees (then perturbed, so folding a
+    non-trivial mean / variance is still exercised), which keeps features O(1) through all ~22 layers, and the heads
+    are scaled so that `pass_fraction` of the anchors clear the score threshold with spread-out scores.
+
+    Why: with random running statistics the features of `demo_weights_` grow to ~1e3 by the last layer, where fp32
+    itself resolves only ~1e-4 -- the north_star's "1e-4 abs on float features" is only a meaningful bar for O(1)
+    features, which is what trained BatchNorm layers produce.  One streaming pass through the layer-by-layer module path
+    (forward pre-hooks on the BN modules, upstream layers already calibrated when a layer is reached)."""
+    import torch
+
+    from det3d_b200.ops.point_cloud.voxelize import Voxelizer
+
+    assert torch.cuda.is_available(), "calibrate_demo_weights_ streams activations through the CUDA module path"
+    dev = torch.device("cuda")
+    model.to(dev).eval()
+    g = torch.Generator().manual_seed(seed + 12345)
+    hooks = []
+
+    def pre_hook(bn, args):
+        x = args[0].detach().float()
+        if x.numel() == 0:
+            return
+        dims = [d for d in range(x.dim()) if d != 1]
+        mean = x.mean(dim=dims)
+        var = x.var(dim=dims, unbiased=False).clamp_min(1e-3)
+        c = mean.shape[0]
+        bn.running_mean.copy_(mean + 0.1 * var.sqrt() * torch.randn(c, generator=g).to(dev))
+        bn.running_var.copy_(var * (0.8 + 0.45 * torch.rand(c, generator=g).to(dev)))
+
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            hooks.append(m.register_forward_pre_hook(pre_hook))
+    vg = cfg.voxel_generator
+    takes_points = cfg.model["reader"]["type"] != "VoxelFeatureExtractorV3"
+    vox = Voxelizer(vg["voxel_size"], vg["range"], vg["max_points_in_voxel"], vg["max_voxel_num"], want_voxels=takes_points,
+                    want_mean=not takes_points)
+    offsets = [0]
+    for c in clouds:
+        offsets.append(offsets[-1] + c.shape[0])
+    pts = torch.from_numpy(np.concatenate(clouds)).to(dev)
+    out = vox(pts, offsets)
+    batch = len(clouds)
+    m_rows = int(out["counts"][batch])
+    coors = out["coors"][:m_rows]
+    grid = [int(v) for v in vox.grid_size]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            if takes_points:
+                feats = model.reader.forward_torch(out["voxels"][:m_rows], out["num_points"][:m_rows], coors)
+                x = model.backbone(feats.reshape(m_rows, -1), coors, batch, grid)
+            else:
+                x = model.backbone.forward_unfused(out["mean"][:m_rows].clone(), coors, batch, grid)
+            if getattr(model, "with_neck", False):
+                x = model.neck(x)
+            thr = float(cfg.test_cfg["score_threshold"])
+            for task in model.bbox_head.tasks:
+                logit = task.conv_cls(x)
+                task.conv_cls.weight.div_(logit.std().clamp_min(1e-6))
+                task.conv_cls.bias.zero_()
+                logit = task.conv_cls(x)
+                best = logit.float().amax(dim=1).reshape(-1) if logit.shape[1] > 1 else logit.float().reshape(-1)
+                # the (1 - pass_fraction) quantile of the best logit lands on the score threshold
+                k = max(1, int(best.numel() * (1.0 - pass_fraction)))
+                q = best.kthvalue(k)[0]
+                task.conv_cls.bias.fill_(float(np.log(thr / (1.0 - thr)) - q))
+                box = task.conv_box(x)
+                task.conv_box.weight.mul_(box_std / box.std().clamp_min(1e-6))
+                task.conv_box.bias.zero_()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+        for h in hooks:
+            h.remove()
+    return model

@@ -217,6 +217,18 @@ int d3b_pillar_features(const float* voxels, const int32_t* num_points, const in
                         int32_t units, const float* weight, const float* scale, const float* shift,
                         float vx, float vy, float x_offset, float y_offset, float* out, void* stream);
 
+/* The same reader fused with the voxelizer: the pillar's points are fetched through the voxelizer's
+ * per-voxel point-index lists, so the [rows, max_points, ndim] voxel tensor is never materialised (call d3b_voxelize
+ * with voxels = NULL).  `lists` = d3b_voxelize_point_lists(...) of the workspace that d3b_voxelize just filled:
+ * [batch][max_voxels][max_points] int32 indices into `points`, >= 0x7f000000 = empty slot; valid until that workspace is
+ * used again.  voxel_counts = d3b_voxelize's per-cloud counts.  Everything else as d3b_pillar_features. */
+const int32_t* d3b_voxelize_point_lists(const d3b_voxel_cfg* cfg, int32_t n_points_total, int32_t batch, void* workspace);
+int d3b_pillar_features_lists(const float* points, const int32_t* lists, const int32_t* voxel_counts, int32_t batch,
+                              int32_t max_voxels, const int32_t* num_points, const int32_t* coors, const int32_t* n_rows,
+                              int32_t row_cap, int32_t max_points, int32_t ndim, int32_t units, const float* weight,
+                              const float* scale, const float* shift, float vx, float vy, float x_offset, float y_offset,
+                              float* out, void* stream);
+
 /* .dense(): rows -> zero-initialised [B, C, D, H, W] (caller zero-fills `out`).
  * replaces SparseConvTensor.dense() at scn.py:192,365. */
 int d3b_sparse_to_dense(const float* feat, const int32_t* coors, const int32_t* n_rows,

@@ -377,3 +377,20 @@ int64_t oracle_rrpn_nms(const float* dets, const int32_t* order, int64_t n, floa
   free(sup);
   return nk;
 }
+
+/* Host greedy sweep of the reference's iou3d NMS, det3d/ops/iou3d/src/iou3d.cpp:103-116: mask [n][col_blocks] u64 as
+ * copied back from nms_kernel, remv accumulates the suppressed columns; keep[] receives the kept (sorted) indices. */
+int64_t oracle_iou3d_host_sweep(const uint64_t* mask, int64_t n, int64_t col_blocks, int64_t* keep) {
+  uint64_t* remv = (uint64_t*)calloc((size_t)(col_blocks > 0 ? col_blocks : 1), sizeof(uint64_t));
+  int64_t nk = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t nblock = i / 64, inblock = i % 64;
+    if (!(remv[nblock] & (1ULL << inblock))) {
+      keep[nk++] = i;
+      const uint64_t* p = mask + i * col_blocks;
+      for (int64_t j = nblock; j < col_blocks; ++j) remv[j] |= p[j];
+    }
+  }
+  free(remv);
+  return nk;
+}

@@ -76,5 +76,19 @@ def host_sweep(mask_np):
     return np.asarray(keep, np.int64)
 
 
+def host_sweep_c(mask_np):
+    """The same sweep in C (oracle/iou3d_oracle.c `oracle_iou3d_host_sweep`), for timing the reference fairly: the
+    reference's own sweep is compiled C++ (iou3d.cpp:103-116)."""
+    from . import build as _build
+    lib = C.CDLL(_build.build())
+    lib.oracle_iou3d_host_sweep.restype = C.c_int64
+    lib.oracle_iou3d_host_sweep.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    m = np.ascontiguousarray(mask_np).view(np.uint64)
+    n, cb = m.shape
+    keep = np.zeros(max(n, 1), np.int64)
+    k = lib.oracle_iou3d_host_sweep(m.ctypes.data, n, cb, keep.ctypes.data)
+    return keep[:k]
+
+
 def nms(boxes_sorted, thresh, normal=False):
     return host_sweep(nms_mask(boxes_sorted, thresh, normal).cpu().numpy())

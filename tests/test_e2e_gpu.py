@@ -16,32 +16,40 @@ def setup():
     from det3d.models import build_detector
     from det3d.torchie import Config
     from det3d_b200.apis import InferencePipeline
-    from det3d_b200.utils.synthetic import demo_weights_
+    from det3d_b200.utils.synthetic import calibrate_demo_weights_, demo_weights_, lidar_like_cloud
     from oracle.second_cpu import SecondCPU
 
     cfg = Config.fromfile(os.path.join(ROOT, "configs", "second_kitti_car.py"))
     torch.manual_seed(0)
-    # random weights calibrated so that ~3 % of the anchors pass the 0.3 threshold with spread scores
+    # random weights made to behave like trained ones: BatchNorm statistics matched to the activations (features stay
+    # O(1), so the north_star's 1e-4 ABSOLUTE tolerance is meaningful), ~3 % of the anchors above the 0.3 threshold
     model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 0)
+    calib = [lidar_like_cloud(20000, cfg.voxel_generator.range, 4, 900 + i) for i in range(2)]
+    calibrate_demo_weights_(model, cfg, calib, 0)
     pipe = InferencePipeline(cfg, model=model, device="cuda")
     cpu = SecondCPU(cfg, model.state_dict(), [a.cpu().numpy() for a in pipe._anchors])
     return cfg, pipe, cpu
 
 
-def _match(cpu_boxes, gpu_boxes, tol=2e-3):
-    if cpu_boxes.shape[0] == 0 or gpu_boxes.shape[0] == 0:
+def _unmatched(want_boxes, got_boxes, tol):
+    """Number of `want` rows without a `got` row within `tol` (max-abs over the box)."""
+    if want_boxes.shape[0] == 0:
         return 0
-    d = (cpu_boxes[:, None, :] - gpu_boxes[None, :, :]).abs().max(-1)[0]
-    return int((d.min(1)[0] <= tol).sum())
+    if got_boxes.shape[0] == 0:
+        return int(want_boxes.shape[0])
+    d = (want_boxes[:, None, :] - got_boxes[None, :, :]).abs().max(-1)[0]
+    return int((d.min(1)[0] > tol).sum())
 
 
 @pytest.mark.parametrize("dist,n", [("lidar", 20000), ("uniform", 20000)])
 def test_forward_matches_cpu_restatement(setup, dist, n):
+    """BASELINE configs[1], stage by stage against the CPU restatement of the reference path, STRICT:
+    indices bit-exact, features <= 1e-4 abs, head outputs <= 1e-4 abs, and the detection list equal to the oracle's."""
     from det3d_b200.utils.synthetic import lidar_like_cloud, uniform_cloud
     cfg, pipe, cpu = setup
     pts = (lidar_like_cloud if dist == "lidar" else uniform_cloud)(n, cfg.voxel_generator.range, 4, 1)
     stages = {}
-    want = cpu.forward([pts], stages)
+    want = cpu.forward([pts], stages)[0]
 
     dev_pts = torch.from_numpy(pts).cuda()
     vox = pipe.voxelizer(dev_pts, [0, n])
@@ -52,20 +60,65 @@ def test_forward_matches_cpu_restatement(setup, dist, n):
     feats_cpu = stages["voxels"].sum(1) / stages["nums"][:, None].astype(np.float32)
     assert np.allclose(vox["mean"][:m].cpu().numpy(), feats_cpu, rtol=0, atol=1e-6)
 
+    model = pipe.model
+    grid = [int(g) for g in pipe.grid_size]
     with torch.no_grad():
-        dense = pipe.model.backbone(vox["mean"], vox["coors"], 1, [int(g) for g in pipe.grid_size],
-                                    n_dev=vox["counts"][1:2])
-    scale = max(1.0, float(stages["dense"].abs().max()))
-    assert float((dense.cpu() - stages["dense"]).abs().max()) <= 1e-4 * scale             # north_star tolerance (abs, O(1) features)
+        dense = model.backbone(vox["mean"], vox["coors"], 1, grid, n_dev=vox["counts"][1:2]).cpu()
+        planes = model.backbone.forward_planes(vox["mean"], vox["coors"], 1, grid, n_dev=vox["counts"][1:2])
+        preds = model.fused_bev().run(planes)[0]
+        heads = {k: v.clone().cpu() for k, v in preds.items()}
+    assert float(stages["dense"].abs().max()) < 100.0, "calibration failed: features are not O(1)"
+    err = float((dense - stages["dense"]).abs().max())
+    assert err <= 1e-4, "dense feature map: abs error %g" % err                              # north_star: 1e-4 ABS
+    for key, ref in (("cls_preds", stages["cls"]), ("box_preds", stages["box"]), ("dir_cls_preds", stages["dirs"])):
+        e = float((heads[key] - ref).abs().max())
+        assert e <= 1e-4, "%s: abs error %g" % (key, e)
 
-    det = pipe.forward_device(dev_pts, [0, n])
-    got = pipe.unpack(pipe.pack(det).cpu())[0]
-    w = want[0]
-    assert w["box3d_lidar"].shape[0] >= 10, "degenerate workload: the CPU restatement found no detections"
-    assert abs(got["box3d_lidar"].shape[0] - w["box3d_lidar"].shape[0]) <= max(2, w["box3d_lidar"].shape[0] // 20)
-    if w["box3d_lidar"].shape[0]:
-        matched = _match(w["box3d_lidar"], got["box3d_lidar"])
-        assert matched >= 0.9 * w["box3d_lidar"].shape[0], "only %d of %d detections match" % (matched, w["box3d_lidar"].shape[0])
+    # the encoder is deterministic: two runs of the whole path give the same bits
+    p1 = pipe.pack(pipe.forward_device(dev_pts, [0, n])).clone()
+    p2 = pipe.pack(pipe.forward_device(dev_pts, [0, n])).clone()
+    assert torch.equal(p1, p2)
+    assert int(pipe.overflow_flag().item()) == 0
+    got = pipe.unpack(p1.cpu())[0]
+
+    # (a) device predict == the ORACLE's predict (mg_head.py:697-1085 restated on the CPU) on the same head outputs:
+    #     same detections, same order
+    o = cpu.predict(heads["box_preds"], heads["cls_preds"], heads["dir_cls_preds"])[0]
+    assert o["box3d_lidar"].shape[0] >= 10, "degenerate workload: no detections"
+    assert got["box3d_lidar"].shape == o["box3d_lidar"].shape
+    assert float((got["box3d_lidar"] - o["box3d_lidar"]).abs().max()) <= 1e-5            # libm vs CUDA exp / atan2 ulps
+    assert float((got["scores"] - o["scores"]).abs().max()) <= 1e-6
+    # (b) against the oracle run from the raw points: the detection SET is identical, except where two candidates'
+    #     scores are closer than the 1e-6-level difference between the two implementations (counted, not ignored)
+    sc = torch.sigmoid(stages["cls"].reshape(-1))
+    top = sc[sc >= cfg.test_cfg.score_threshold].sort(descending=True)[0][: cfg.test_cfg.nms.nms_pre_max_size]
+    fragile = int(((top[:-1] - top[1:]) < 2e-6).sum()) + int(((sc - cfg.test_cfg.score_threshold).abs() < 2e-6).sum())
+    missing = _unmatched(want["box3d_lidar"], got["box3d_lidar"], 1e-3)
+    extra = _unmatched(got["box3d_lidar"], want["box3d_lidar"], 1e-3)
+    assert want["box3d_lidar"].shape[0] >= 10
+    assert missing <= fragile and extra <= fragile, "detections differ (%d missing, %d extra) with only %d near-tied candidates" % (
+        missing, extra, fragile)
+
+
+def test_tf32x3_fallback_path_and_overflow_guard(setup):
+    """The round-1 kernels stay selectable (`set_math("tf32x3")`) and are where a forward is re-run when a feature
+    leaves the f16 range: same detections as the FP16x3 path, and the guard trips (instead of saturating) on huge inputs."""
+    from det3d_b200.ops.spconv import conv16
+    from det3d_b200.utils.synthetic import lidar_like_cloud
+    cfg, pipe, cpu = setup
+    cloud = torch.from_numpy(lidar_like_cloud(12000, cfg.voxel_generator.range, 4, 77))
+    a = pipe.unpack(pipe.infer_host([cloud]).clone())[0]
+    pipe.model.set_math("tf32x3")
+    pipe.model.backbone.fused().deterministic = True
+    try:
+        b = pipe.unpack(pipe.infer_host([cloud]).clone())[0]
+    finally:
+        pipe.model.set_math("fp16x3")
+        pipe.model.backbone.fused().deterministic = False
+    assert a["box3d_lidar"].shape[0] >= 5 and _unmatched(a["box3d_lidar"], b["box3d_lidar"], 1e-3) <= 1
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    conv16.Planes.from_f32(torch.full((4, 8), 7.0e4, device="cuda"), flag)
+    assert int(flag.item()) == 1
 
 
 def test_host_api_and_batching(setup):
@@ -132,58 +185,75 @@ def test_fused_bev_path_matches_cudnn_path(setup):
         assert float((a - r).abs().max()) <= 1e-4 * max(1.0, float(r.abs().max())), key
 
 
-def test_cbgs_nuscenes_config_batch2():
-    """BASELINE config 4 shape: CBGS (SpMiddleResNetFHD, 2-block RPN, 6 task heads, 9-dim boxes with
-    angle-vector encoding), 35k-point 5-feature clouds, batch of 2.  The backbone is checked against the
-    oracle elsewhere (test_spconv_gpu); here the device-side predict is checked against the CPU restatement
-    of MultiGroupHead.predict fed with the same head outputs."""
+def test_cbgs_nuscenes_config():
+    """BASELINE configs[3] shape: CBGS (SpMiddleResNetFHD with residual blocks, two-block RPN with a stride-2 block and a
+    ConvTranspose deblock, 6 task heads, 9-dim boxes with angle-vector encoding), 35k-point 5-feature clouds, 4 clouds
+    per GPU as in the 32-over-8 sharding.  RPN + heads run on the FP16x3 TMA kernels and are checked against the module's
+    fp32 cuDNN forward; the device predict is checked against the CPU restatement of MultiGroupHead.predict on the same
+    head outputs: identical detections.  (The sparse encoder is pinned against the oracle in test_spconv_gpu; the
+    32-cloud multi-GPU run in test_multi_gpu.)"""
     from det3d.models import build_detector
     from det3d.torchie import Config
     from det3d_b200.apis import InferencePipeline
-    from det3d_b200.utils.synthetic import demo_weights_, lidar_like_cloud
+    from det3d_b200.utils.synthetic import calibrate_demo_weights_, demo_weights_, lidar_like_cloud
     from oracle.predict_cpu import predict_sample_task
 
     cfg = Config.fromfile(os.path.join(ROOT, "configs", "cbgs_nusc.py"))
     torch.manual_seed(1)
-    model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 1, cls_bias=-2.4)
+    model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 1)
+    calibrate_demo_weights_(model, cfg, [lidar_like_cloud(35000, cfg.voxel_generator.range, 5, 50 + i) for i in range(2)], 1,
+                            pass_fraction=0.01)
     pipe = InferencePipeline(cfg, model=model, device="cuda")
-    assert pipe.model.fused_bev() is None          # strided RPN with a ConvTranspose deblock: torch path
-    clouds = [lidar_like_cloud(35000, cfg.voxel_generator.range, 5, s) for s in (0, 1)]
+    B = 4
+    assert type(pipe.model.fused_bev()).__name__ == "FusedBevStack"        # strided RPN + ConvTranspose on own kernels
+    clouds = [lidar_like_cloud(35000, cfg.voxel_generator.range, 5, s) for s in range(B)]
     pts = torch.from_numpy(np.concatenate(clouds)).cuda()
-    offsets = [0, 35000, 70000]
+    offsets = [35000 * i for i in range(B + 1)]
     det = pipe.forward_device(pts, offsets)
-    assert det["boxes"].shape == (2, 6 * 83, 9) and int(det["valid"].sum()) > 20
+    assert det["boxes"].shape == (B, 6 * 83, 9) and int(det["valid"].sum()) > 20
+    got = pipe.unpack(pipe.pack(det).cpu())
+    assert int(pipe.overflow_flag().item()) == 0
 
-    # one set of head outputs -> device predict vs the CPU restatement of predict.  (The encoder is not
-    # re-run for the comparison: its pair-based layers sum with fp32 atomics, so two runs differ in the
-    # last bits and near-tied random-weight scores may reorder.)
-    with torch.no_grad():
-        vox = pipe.voxelizer(pts, offsets)
-        counts = vox["counts"].cpu().numpy()
-        assert counts[2] == counts[0] + counts[1] and counts[0] > 10000
-        x = model.backbone(vox["mean"], vox["coors"], 2, [int(g) for g in pipe.grid_size], n_dev=vox["counts"][2:3])
-        preds = model.bbox_head(model.neck(x))
-        det2 = model.bbox_head.predict_device(dict(anchors=pipe.anchors(2)), preds, cfg.test_cfg)
-    got = pipe.unpack(pipe.pack(det2).cpu())
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            vox = pipe.voxelizer(pts, offsets)
+            counts = vox["counts"].cpu().numpy()
+            assert counts[B] == counts[:B].sum() and counts[0] > 10000
+            grid = [int(g) for g in pipe.grid_size]
+            planes = model.backbone.forward_planes(vox["mean"], vox["coors"], B, grid, n_dev=vox["counts"][B:B + 1])
+            dense = model.backbone(vox["mean"], vox["coors"], B, grid, n_dev=vox["counts"][B:B + 1])
+            assert torch.equal(planes.to_f32().permute(0, 3, 1, 2), dense)
+            preds = [{k: v.clone() for k, v in d.items()} for d in model.fused_bev().run(planes)]
+            ref = model.bbox_head(model.neck(dense))                       # torch modules: fp32 cuDNN
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert float(dense.abs().max()) < 100.0
+    for t in range(6):
+        for key in ("box_preds", "cls_preds", "dir_cls_preds"):
+            e = float((preds[t][key] - ref[t][key]).abs().max())
+            assert e <= 1e-4, "task %d %s: abs error %g vs fp32 cuDNN" % (t, key, e)
+
     flag = 0
-    want = [dict(b=[], s=[], l=[]) for _ in range(2)]
+    want = [dict(b=[], s=[], l=[]) for _ in range(B)]
     for task_id, p in enumerate(preds):
         anchors = pipe._anchors[task_id].cpu()
         n_cls = model.bbox_head.num_classes[task_id]
-        for b in range(2):
+        for b in range(B):
             bx, sc, lb = predict_sample_task(p["cls_preds"][b].reshape(-1, n_cls).cpu(), p["box_preds"][b].reshape(-1, 10).cpu(),
-                                             None, anchors, cfg.test_cfg, True)
+                                             p["dir_cls_preds"][b].reshape(-1, 2).cpu() if "dir_cls_preds" in p else None,
+                                             anchors, cfg.test_cfg, True)
             want[b]["b"].append(bx); want[b]["s"].append(sc); want[b]["l"].append(lb + flag)
         flag += n_cls
-    for b in range(2):
-        wb, wl = torch.cat(want[b]["b"]), torch.cat(want[b]["l"])
-        gb, gl = got[b]["box3d_lidar"], got[b]["label_preds"]
-        assert wb.shape[0] >= 10
-        assert abs(gb.shape[0] - wb.shape[0]) <= max(3, wb.shape[0] // 20)
-        d = (wb[:, None, :] - gb[None, :, :]).abs().max(-1)[0]
-        j = d.argmin(1)
-        ok = (d.min(1)[0] <= 2e-3) & (gl[j] == wl)
-        assert int(ok.sum()) >= 0.9 * wb.shape[0]
+    total = 0
+    for b in range(B):
+        wb, ws, wl = torch.cat(want[b]["b"]), torch.cat(want[b]["s"]), torch.cat(want[b]["l"])
+        gb, gs, gl = got[b]["box3d_lidar"], got[b]["scores"], got[b]["label_preds"]
+        assert gb.shape == wb.shape, "sample %d: %d detections vs %d from the oracle" % (b, gb.shape[0], wb.shape[0])
+        assert float((gb - wb).abs().max()) <= 1e-5 and float((gs - ws).abs().max()) <= 1e-6 and torch.equal(gl, wl)
+        total += wb.shape[0]
+    assert total >= 40
 
 
 def test_fused_predict_kernels_match_torch_ops(setup):

@@ -60,3 +60,31 @@ def test_c_oracle_matches_live_reference_on_fresh_seeds():
         a = ref.points_to_voxel(pts, vs, pcr, 5, True, 600 + 700 * seed)
         b = ovoxel.points_to_voxel(pts, vs, pcr, 5, True, 600 + 700 * seed)
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_c_oracle_equals_aot_reference_kernel_on_random_inputs():
+    """Beyond the committed goldens: when oracle/_ref holds the reference's own numba kernel compiled ahead of time
+    (oracle/build.py, built where /root/reference exists), the C restatement must reproduce it bit for bit on fresh
+    seeded clouds -- boundary-snapped points, overflow `break`, ndim 3/4/5, an empty cloud."""
+    from oracle import voxel, voxel_ref
+
+    if not voxel_ref.available():
+        pytest.skip("oracle/_ref/ref_voxel_aot*.so not built (reference checkout absent at build time)")
+    rng = np.random.default_rng(123)
+    cases = [([0.05, 0.05, 0.1], [0, -40.0, -3.0, 70.4, 40.0, 1.0], 5, 20000, 4, 30000),
+             ([0.16, 0.16, 4.0], [0, -39.68, -3, 69.12, 39.68, 1], 100, 1200, 4, 9000),      # hits the max_voxels break
+             ([0.1, 0.1, 0.2], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], 10, 60000, 5, 20000),
+             ([0.05, 0.05, 0.1], [0, -40.0, -3.0, 70.4, 40.0, 1.0], 5, 20000, 3, 0)]
+    for vs, pcr, max_pts, max_vox, ndim, n in cases:
+        lo, hi = np.asarray(pcr[:3], np.float32), np.asarray(pcr[3:], np.float32)
+        span = (hi - lo + 2.0)[[0, 1, 2] + [0] * (ndim - 3)]
+        base = (lo - 1.0)[[0, 1, 2] + [0] * (ndim - 3)]
+        pts = (base + rng.random((n, ndim)).astype(np.float32) * span).astype(np.float32)      # ~ +-1 m beyond the range
+        if n:
+            snap = rng.random(n) < 0.3            # exact multiples of the voxel size: fp32 division edge cases
+            cell = np.floor((pts[snap, :3] - lo) / np.asarray(vs, np.float32))
+            pts[snap, :3] = lo + cell * np.asarray(vs, np.float32)
+        want = voxel_ref.points_to_voxel(pts, vs, pcr, max_pts, True, max_vox)
+        got = voxel.points_to_voxel(pts, vs, pcr, max_pts, True, max_vox)
+        for a, b in zip(got, want):
+            assert a.dtype == b.dtype and np.array_equal(a, b)

@@ -102,41 +102,77 @@ def test_fused_reader_other_shapes(ndim, units):
 
 @pytest.mark.gpu
 def test_pointpillars_pipeline_matches_cpu_restatement():
-    """BASELINE config 3 shape (uniform clouds that hit the 12000-pillar cap) at B=2; device pipeline vs the CPU
-    restatement stage by stage."""
+    """BASELINE configs[2] at its stated size: 20k-point clouds, batch 8, uniform clouds that hit the 12000-pillar cap
+    (the reference `break`).  Device pipeline vs the CPU restatement stage by stage, STRICT: indices and point lists
+    bit-exact, pillar features / RPN / head outputs <= 1e-4 abs, detections identical to the oracle's predict on the same
+    head outputs, and the detection set equal to the from-scratch oracle's up to near-tied candidates (counted)."""
     from det3d.models import build_detector
     from det3d.torchie import Config
     from det3d_b200.apis import InferencePipeline
-    from det3d_b200.utils.synthetic import demo_weights_, uniform_cloud
+    from det3d_b200.utils.synthetic import calibrate_demo_weights_, demo_weights_, lidar_like_cloud, uniform_cloud
     from oracle.pillars_cpu import PillarsCPU
 
     cfg = Config.fromfile(os.path.join(ROOT, "configs", "pointpillars_kitti_car.py"))
     torch.manual_seed(0)
-    # head scales calibrated on the CPU restatement: a few % of the 107k anchors pass the 0.05 threshold
-    model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 0, cls_scale=0.3,
-                          cls_bias=-3.6, box_scale=0.02)
+    model = demo_weights_(build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval(), 0)
+    calibrate_demo_weights_(model, cfg, [uniform_cloud(20000, cfg.voxel_generator.range, 4, 70),
+                                         lidar_like_cloud(20000, cfg.voxel_generator.range, 4, 71)], 0, pass_fraction=0.02)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     pipe = InferencePipeline(cfg, model=model, device="cuda")
+    assert type(pipe.model.fused_bev()).__name__ == "FusedBevStack"        # [3,5,5] RPN with strides + ConvTranspose on own kernels
     cpu = PillarsCPU(cfg, sd, [a.cpu().numpy() for a in pipe._anchors])
-    clouds = [uniform_cloud(20000, cfg.voxel_generator.range, 4, 7), uniform_cloud(9000, cfg.voxel_generator.range, 4, 8)]
+    B = 8
+    clouds = [uniform_cloud(20000, cfg.voxel_generator.range, 4, 7 + i) if i % 2 == 0 else
+              lidar_like_cloud(20000, cfg.voxel_generator.range, 4, 7 + i) for i in range(B)]
     stages = {}
     want = cpu.forward(clouds, stages)
     assert (stages["coors"][:, 0] == 0).sum() == 12000                      # the reference `break` at max_voxels
 
     packed = pipe.infer_host([torch.from_numpy(c) for c in clouds])
     got = pipe.unpack(packed)
+    assert int(pipe.overflow_flag().item()) == 0
+    offsets = [20000 * i for i in range(B + 1)]
     pts = torch.from_numpy(np.concatenate(clouds)).cuda()
-    vox = pipe.voxelizer(pts, [0, 20000, 29000])
-    m = int(vox["counts"][2])
+    from det3d_b200.ops.point_cloud.voxelize import Voxelizer
+    vg = cfg.voxel_generator
+    assert pipe._reader_takes_lists and pipe.voxelizer.want_voxels is False     # the serving path never builds [M,100,4]
+    full = Voxelizer(vg.voxel_size, vg.range, vg.max_points_in_voxel, vg.max_voxel_num, want_voxels=True, want_mean=False)
+    vox = full(pts, offsets)
+    m = int(vox["counts"][B])
     assert np.array_equal(vox["coors"][:m].cpu().numpy(), stages["coors"])
     assert np.array_equal(vox["num_points"][:m].cpu().numpy(), stages["nums"])
     assert np.array_equal(vox["voxels"][:m].cpu().numpy(), stages["voxels"])
     with torch.no_grad():
-        feats = pipe.model.reader(vox["voxels"], vox["num_points"], vox["coors"], n_dev=vox["counts"][2:3])
+        feats = pipe.model.reader(vox["voxels"], vox["num_points"], vox["coors"], n_dev=vox["counts"][B:B + 1])
+        # the reader fused with the voxelizer (point-index lists instead of the voxel tensor): the same bits
+        lean = pipe.voxelizer(pts, offsets)
+        assert lean["voxels"] is None and torch.equal(lean["coors"][:m], vox["coors"][:m])
+        fused = pipe.model.reader.forward_lists(dict(lean["point_lists"], counts=lean["counts"]), lean["num_points"],
+                                                lean["coors"], lean["coors"].shape[0], lean["counts"][B:B + 1])
+        assert torch.equal(fused[:m], feats[:m])
+        planes = pipe.model.backbone.forward_planes(feats, vox["coors"], B, [int(g) for g in pipe.grid_size], n_dev=vox["counts"][B:B + 1])
+        preds = {k: v.clone().cpu() for k, v in pipe.model.fused_bev().run(planes)[0].items()}
     assert float((feats[:m].cpu() - stages["pillar_feats"]).abs().max()) <= 1e-4
-    for b in range(2):
-        w, gdet = want[b], got[b]
-        assert abs(w["box3d_lidar"].shape[0] - gdet["box3d_lidar"].shape[0]) <= max(2, w["box3d_lidar"].shape[0] // 20)
-        if w["box3d_lidar"].shape[0]:
-            d = (w["box3d_lidar"][:, None, :] - gdet["box3d_lidar"][None, :, :]).abs().max(-1)[0]
-            assert float((d.min(1)[0] <= 2e-3).float().mean()) >= 0.9
+    assert float(stages["rpn"].abs().max()) < 100.0, "calibration failed: features are not O(1)"
+    for key, ref in (("cls_preds", stages["cls"]), ("box_preds", stages["box"]), ("dir_cls_preds", stages["dirs"])):
+        e = float((preds[key] - ref).abs().max())
+        assert e <= 1e-4, "%s: abs error %g" % (key, e)
+    o = cpu.predict(preds["box_preds"], preds["cls_preds"], preds["dir_cls_preds"])
+    thr, pre = cfg.test_cfg.score_threshold, cfg.test_cfg.nms.nms_pre_max_size
+    total = 0
+    for b in range(B):
+        assert got[b]["box3d_lidar"].shape == o[b]["box3d_lidar"].shape, "sample %d" % b
+        if o[b]["box3d_lidar"].shape[0]:
+            assert float((got[b]["box3d_lidar"] - o[b]["box3d_lidar"]).abs().max()) <= 1e-5
+            assert float((got[b]["scores"] - o[b]["scores"]).abs().max()) <= 1e-6
+        total += o[b]["box3d_lidar"].shape[0]
+        sc = torch.sigmoid(stages["cls"][b].reshape(-1))
+        top = sc[sc >= thr].sort(descending=True)[0][:pre]
+        fragile = int(((top[:-1] - top[1:]) < 2e-6).sum()) + int(((sc - thr).abs() < 2e-6).sum())
+        w, gdet = want[b]["box3d_lidar"], got[b]["box3d_lidar"]
+        for a_, b_ in ((w, gdet), (gdet, w)):
+            miss = 0
+            if a_.shape[0]:
+                miss = a_.shape[0] if b_.shape[0] == 0 else int(((a_[:, None, :] - b_[None, :, :]).abs().max(-1)[0].min(1)[0] > 1e-3).sum())
+            assert miss <= fragile, "sample %d: %d detections differ with %d near-tied candidates" % (b, miss, fragile)
+    assert total >= 40
