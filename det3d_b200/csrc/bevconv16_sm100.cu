@@ -16,9 +16,13 @@
 //    stage.  In a patch, eight consecutive 128-byte rows are one image row segment, so the matrix for kernel row ky is
 //    the SAME staged patch with the UMMA descriptor start advanced by ky * 1024 bytes: one patch load per (kx, 64
 //    channels) serves three (ky, kx) offsets.
-//  * FP16x3: per k-step two MMAs, A_hi x [B_hi | B_lo] (N = 2 C_out) and A_lo x B_hi (N = C_out), fp32 accumulation
-//    in TMEM (all 512 columns at C_out = 128); the epilogue adds the two column halves and applies bias / BN / ReLU.
-//  * Warp roles: 1 TMA warp, 1 MMA warp, 8 epilogue warps (one per TMEM quadrant and half); A ring of 2 stages
+//  * FP16x3: per k-step three MMAs (A_lo.B_hi, A_hi.B_lo, A_hi.B_hi) with fp32 accumulation in TMEM -- but only
+//    across ONE weight stage (12 MMAs): the tensor core truncates on every accumulation, and chaining all 72+ k-steps of a
+//    3x3x128 reduction into one accumulator shrank the outputs by ~4e-6 per layer (measured: error proportional to chain
+//    length), which 20 layers turn into > 1e-4.  Each stage therefore starts from zero in its own TMEM buffer pair (two
+//    pairs: stage s+1 accumulates while stage s is drained) and eight accumulator warps add the stages in fp32 registers
+//    with round-to-nearest, then apply bias / BN / ReLU and write the f16 planes.
+//  * Warp roles: 1 TMA warp, 1 MMA warp, 8 accumulator warps (one per TMEM quadrant and half); A ring of 2 stages
 //    (4 patches each), B ring of 2..4 stages, all mbarrier-driven; persistent grid (143 tiles at 200 x 176).
 //  * stride 2 (RPN down-sampling blocks): the box is loaded with elementStrides = 2, one load per (ky, kx).
 //  * groups: several weight blocks over the same input in one launch -- C_out = 256 as two N = 128 passes, and
@@ -55,8 +59,8 @@ struct BvCfg {
   static constexpr int kAStageBytes = 4 * kPatchBytes;                                // {half 0, half 1} x {hi, lo}
   static constexpr int kBBytes = 2 * COUT * 128;                                      // [B_hi rows | B_lo rows]
   static constexpr int kBStages = COUT >= 128 ? 2 : 4;
-  static constexpr int kAccCols = 2 * COUT;                                           // per half
-  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;             // both halves
+  static constexpr int kAccCols = COUT;                                               // one (stage, half) accumulator
+  static constexpr int kTmemCols = 4 * kAccCols;                                      // {2 buffers} x {2 halves}: 128 .. 512
   static constexpr int kSmemBytes = kBvAStages * kAStageBytes + kBStages * kBBytes + 1024 + 256;
   // with stride 1 one A stage serves the KS kernel rows of a (kx, kb); with stride 2 every (ky, kx) has its own
   static constexpr int kRowsPerAStage = STRIDE == 1 ? KS : 1;
@@ -93,9 +97,9 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   auto a_empty = [&](int s) { return bar_base + 8u * (kBvAStages + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * kBvAStages + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * kBvAStages + Cfg::kBStages + s); };
-  const uint32_t acc_full = bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages);
-  const uint32_t acc_empty = acc_full + 8u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kBvAStages + 2 * Cfg::kBStages + 2));
+  auto acc_full = [&](uint32_t b) { return bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages + b); };
+  auto acc_empty = [&](uint32_t b) { return bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kBvAStages + 2 * Cfg::kBStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_group = g.batch * g.tiles_y * g.tiles_x;
@@ -105,8 +109,10 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBvAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 256);         // the eight epilogue warps
+    for (uint32_t b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);       // tcgen05.commit of one weight stage's MMAs
+      mbar_init(acc_empty(b), 256);    // the eight accumulator warps have read that stage's partial sums
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
@@ -173,13 +179,12 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
     }
   } else if (warp == kBvMmaWarp) {
     // ===================== MMA issuer (one elected lane) =====================
-    constexpr uint32_t idesc2 = umma_idesc_f16(128, 2 * COUT);   // A_hi x [B_hi | B_lo]
-    constexpr uint32_t idesc1 = umma_idesc_f16(128, COUT);       // A_lo x B_hi
-    uint32_t a_it = 0, b_it = 0, tile_it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-      D3B_WAIT(acc_empty, (tile_it & 1u) ^ 1u, 3);
-      tc_fence_after();
-      uint32_t accumulate = 0;
+    // Every weight stage (one (ky, kx, 64-channel slice), both halves) is accumulated from zero in its own pair of TMEM
+    // buffers: the chain of truncating tensor-core accumulations is 12 MMAs long, the stages are summed by the
+    // accumulator warps in fp32 registers with round-to-nearest.
+    constexpr uint32_t idesc = umma_idesc_f16(128, COUT);
+    uint32_t a_it = 0, b_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < g.n_kb; ++kb) {
         const int n_ks = min(kBvKc / 16, (g.c_in - kb * kBvKc + 15) / 16);
         for (int kx = 0; kx < KS; ++kx) {
@@ -188,27 +193,32 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
             D3B_WAIT(a_full(sa), (a_it / kBvAStages) & 1u, 4);
             for (int r = 0; r < Cfg::kRowsPerAStage; ++r, ++b_it) {
               const int sb = b_it % Cfg::kBStages;
+              const uint32_t buf = b_it & 1u;
+              D3B_WAIT(acc_empty(buf), ((b_it >> 1) & 1u) ^ 1u, 3);
               D3B_WAIT(b_full(sb), (b_it / Cfg::kBStages) & 1u, 5);
               tc_fence_after();
               if (lane == 0) {
-                const uint32_t bt = b_base + sb * Cfg::kBBytes;
+                const uint32_t b_hi = b_base + sb * Cfg::kBBytes;
+                const uint32_t b_lo = b_hi + COUT * 128;
                 // stride 1: kernel row r of the staged patch = the same bytes 8 rows (1024 B) further down
                 const uint32_t row_adv = STRIDE == 1 ? (uint32_t)(ky0 + r) * 1024u : 0u;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                   const uint32_t ah = a_base + sa * Cfg::kAStageBytes + (2 * half) * Cfg::kPatchBytes + row_adv;
                   const uint32_t al = ah + Cfg::kPatchBytes;
-                  const uint32_t d_addr = tmem_d + half * Cfg::kAccCols;
+                  const uint32_t d_addr = tmem_d + (buf * 2 + half) * Cfg::kAccCols;
                   for (int ks = 0; ks < n_ks; ++ks) {
                     const uint32_t adv = ks * 32;
-                    tc_mma_f16(d_addr, umma_desc_sw128(ah + adv), umma_desc_sw128(bt + adv), idesc2, accumulate | (uint32_t)(ks > 0));
-                    tc_mma_f16(d_addr, umma_desc_sw128(al + adv), umma_desc_sw128(bt + adv), idesc1, 1u);
+                    // small terms first, the dominant hi.hi product last
+                    tc_mma_f16(d_addr, umma_desc_sw128(al + adv), umma_desc_sw128(b_hi + adv), idesc, ks > 0 ? 1u : 0u);
+                    tc_mma_f16(d_addr, umma_desc_sw128(ah + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
+                    tc_mma_f16(d_addr, umma_desc_sw128(ah + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
                   }
                 }
                 tc_commit(b_empty(sb));
+                tc_commit(acc_full(buf));
               }
               __syncwarp();
-              accumulate = 1u;
             }
             if (lane == 0) tc_commit(a_empty(sa));
             __syncwarp();
@@ -216,39 +226,49 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
           }
         }
       }
-      if (lane == 0) tc_commit(acc_full);
-      __syncwarp();
     }
   } else {
-    // ===================== epilogue: TMEM -> bias / BN / ReLU -> NHWC planes =====================
+    // ===================== accumulator warps: TMEM partial sums -> fp32 registers -> bias / BN / ReLU -> NHWC planes =====
     const int ew = warp - kBvEpiWarp0;          // 0..7
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
     const int half = ew >> 2;
     const int m = quad * 32 + lane;             // pixel of the half: row m / 8, column m % 8
+    const int n_stages = g.n_kb * k_vol;        // weight stages per tile
     bool ovf = false;
-    uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    uint32_t b_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       int grp, b, y0, x0;
       decode(tile, grp, b, y0, x0);
+      float acc[COUT];
+#pragma unroll
+      for (int q = 0; q < COUT; ++q) acc[q] = 0.f;
+#pragma unroll 1
+      for (int st = 0; st < n_stages; ++st, ++b_it) {
+        const uint32_t buf = b_it & 1u;
+        D3B_WAIT(acc_full(buf), (b_it >> 1) & 1u, 6);
+        tc_fence_after();
+        const uint32_t t0 = tmem_d + (buf * 2 + half) * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(t0 + c0, r);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + q] += __uint_as_float(r[q]);
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));
+      }
       const int y = y0 + (m >> 3), x = x0 + half * kBvHalfX + (m & 7);
-      const bool live = y < g.h_out && x < g.w_out;
+      if (!(y < g.h_out && x < g.w_out)) continue;
       const int cg = grp % g.cgroups, ug = grp / g.cgroups;
       const int oy = y * g.up + ug / g.up, ox = x * g.up + ug % g.up;
       const size_t row_off = (((size_t)b * g.out_h + oy) * g.out_w + ox) * (size_t)g.out_channels + g.out_c0 + cg * COUT;
       const int pcol = grp * COUT;              // per-group epilogue parameters are laid out group-major
-      D3B_WAIT(acc_full, tile_it & 1u, 6);
-      tc_fence_after();
-      const uint32_t t0 = tmem_d + half * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
-        uint32_t r1[16], r2[16];
-        tc_ld16_nowait(t0 + c0, r1);
-        tc_ld16_nowait(t0 + COUT + c0, r2);
-        tc_ld_wait();
-        if (!live) continue;
-        float v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = (__uint_as_float(r1[q]) + __uint_as_float(r2[q])) * epi.acc_scale;
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        float* v = acc + c0;                      // in place: the running sums of this chunk are dead afterwards
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] *= epi.acc_scale;
         if (epi.bias) {
 #pragma unroll
           for (int q = 0; q < 16; q += 4) {
@@ -259,10 +279,10 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         if (epi.scale) {
 #pragma unroll
           for (int q = 0; q < 16; q += 4) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(epi.scale + pcol + c0 + q));
-            const float4 t = __ldg(reinterpret_cast<const float4*>(epi.shift + pcol + c0 + q));
-            v[q] = fmaf(v[q], s.x, t.x); v[q + 1] = fmaf(v[q + 1], s.y, t.y);
-            v[q + 2] = fmaf(v[q + 2], s.z, t.z); v[q + 3] = fmaf(v[q + 3], s.w, t.w);
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(epi.scale + pcol + c0 + q));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(epi.shift + pcol + c0 + q));
+            v[q] = fmaf(v[q], sc.x, sh.x); v[q + 1] = fmaf(v[q + 1], sc.y, sh.y);
+            v[q + 2] = fmaf(v[q + 2], sc.z, sh.z); v[q + 3] = fmaf(v[q + 3], sc.w, sh.w);
           }
         }
         if (epi.relu) {
@@ -293,8 +313,6 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
           for (int q = 0; q < 16; q += 4) pf[q >> 2] = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
         }
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty);
     }
     if (ovf && overflow) atomicOr(overflow, 1);
   }

@@ -19,14 +19,20 @@
 // two f16 planes, hi = f16(x) and lo = f16(x - hi) (22 significant bits, written once by the producing layer's
 // epilogue); weights are split the same way at load time after an exact power-of-two scaling that keeps their lo
 // parts out of the f16 subnormal range.  D += A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with fp32 accumulation; the dropped
-// lo.lo term is 2^-22 relative.  The three products take TWO MMAs per k-step: B_hi and B_lo are stacked along N
-// ([B_hi | B_lo], N = 2*C_out) so A_hi is read from shared memory once for both, and A_lo x B_hi (N = C_out) lands on
-// the first half of the columns; the epilogue adds the two halves.  |x| >= 65504 cannot be represented: the epilogue
-// raises a device flag instead of silently saturating (the host checks it with the detections).
+// lo.lo term is 2^-22 relative.  |x| >= 65504 cannot be represented: the epilogue raises a device flag instead of
+// silently saturating (the host checks it with the detections).
 //
-// Roles: one gather group of 4 warps per pipeline stage (slot j -> group j % stages; 4 stages, 3 at C_out = 128), 1 MMA
-// warp (also owns TMEM), 4 epilogue warps; two TMEM accumulators so the drain of tile t overlaps the MMAs of tile t+1;
-// persistent grid <= 148 CTAs.
+// Accumulation.  The tensor core adds every MMA's partial sum into the fp32 TMEM accumulator with truncation (round
+// toward zero): measured on this path, the relative error of a layer grew linearly with the number of MMAs chained into
+// one accumulator (27 offsets x 8..24 MMAs -> 2e-5 .. 7e-5 over the encoder), a systematic shrink that 20 layers turn
+// into > 1e-4.  So the chain is cut at ONE pipeline slot (<= 12 MMAs): each slot accumulates from zero in its own TMEM
+// buffer (two buffers, so slot j+1 runs while slot j is drained) and dedicated accumulator warps add the slots'
+// partial sums into fp32 registers with round-to-nearest -- the same summation structure as the reference's
+// per-offset GEMM + scatter-add, with a fixed order.
+//
+// Roles: 4 or 8 accumulator warps (TMEM -> registers every slot, fused epilogue at the end of the tile), one gather
+// group of 2 warps per pipeline stage (slot j -> group j % stages; 4 stages, 3 at C_out = 128; pure cp.async issue, so few
+// threads suffice and the register file goes to the accumulators), 1 MMA warp (also owns TMEM); persistent grid <= 148 CTAs.
 // Algorithmic bytes per layer: N_in*C_in*4 + N_out*C_out*4 + P*8 + K*C_in*C_out*4.
 #include "umma.cuh"
 
@@ -46,11 +52,16 @@ struct OsCfg {
   // the stage go by -- with more groups than stages a group would meet a stage it last touched two uses ago, read a
   // stale parity as "free" and overwrite live operands.)
   static constexpr int kGroups = kStages;
-  static constexpr int kMmaWarp = 4 * kGroups;             // TMEM alloc + MMA issue
-  static constexpr int kEpiWarp0 = kMmaWarp + 1;           // four epilogue warps, warp & 3 = its TMEM lane quadrant
-  static constexpr int kThreads = 32 * (kEpiWarp0 + 4);    // 544 (3 groups) / 672 (4 groups)
-  static constexpr int kAccCols = 2 * COUT;                // [hi.hi + lo.hi | hi.lo]
-  static constexpr int kTmemCols = 2 * kAccCols;           // double-buffered across tiles (64 .. 512, a power of two)
+  // Accumulator warps: every TMEM lane quadrant is served by kEpiWarps / 4 warps, each owning kCols columns of the
+  // output row its lane stands for (the running fp32 sums live in registers, see the kernel comment).
+  static constexpr int kEpiWarps = COUT >= 64 ? 8 : 4;
+  static constexpr int kCols = COUT / (kEpiWarps / 4);     // columns per accumulator thread: 16, 32, 32, 64
+  static constexpr int kGatherWarp0 = kEpiWarps;           // warps [kEpiWarps, kEpiWarps + 2 kGroups): gather groups of 2 warps
+  static constexpr int kGroupThreads = 64;                 // (few threads: the register file goes to the accumulators)
+  static constexpr int kMmaWarp = kEpiWarps + 2 * kGroups; // TMEM alloc + MMA issue
+  static constexpr int kThreads = 32 * (kMmaWarp + 1);     // 416 (C_out 16/32), 544 (64), 480 (128)
+  static constexpr int kAccCols = COUT < 32 ? 32 : COUT;   // one per-slot accumulator
+  static constexpr int kTmemCols = 2 * kAccCols;           // two of them: slot j+1 accumulates while slot j is drained
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 32 * kOsTileM * 4;
 };
 
@@ -160,12 +171,12 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 128 + 1);   // the 128 gather threads of one group + the expect_tx arrive
+      mbar_init(full_bar(s), Cfg::kGroupThreads + 1);   // the gather threads of one group + the expect_tx arrive
       mbar_init(empty_bar(s), 1);        // tcgen05.commit
     }
     for (uint32_t b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 128);
+      mbar_init(acc_full(b), 1);                       // tcgen05.commit of a slot's MMAs
+      mbar_init(acc_empty(b), 32 * Cfg::kEpiWarps);    // every accumulator warp has read the slot's partial sums
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -180,16 +191,55 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
-  uint32_t tile_it = 0;   // accumulator phase counter
-
-  if (warp < Cfg::kMmaWarp) {
+  if (warp < Cfg::kEpiWarps) {
+    // ===================== accumulator warps =====================
+    // Per slot: TMEM partial sums -> fp32 registers (round-to-nearest adds).  At the end of the tile: fused
+    // bias / BN / residual / ReLU, split into f16 planes, one store per output row.
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int col0 = (warp >> 2) * Cfg::kCols;       // first output column owned by this thread
+    bool ovf = false;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n_slots = __popc(tile_mask[tile]) * n_kb;
+      const int o = tile * kOsTileM + quad * 32 + lane;
+      float acc[Cfg::kCols];
+#pragma unroll
+      for (int q = 0; q < Cfg::kCols; ++q) acc[q] = 0.f;
+      for (int j = 0; j < n_slots; ++j, ++it) {
+        const uint32_t buf = it & 1u;
+        D3B_WAIT(acc_full(buf), (it >> 1) & 1u, 4);
+        tc_fence_after();
+        const uint32_t t0 = tmem_d + buf * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16) + col0;
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::kCols; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(t0 + c0, r);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + q] += __uint_as_float(r[q]);
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));               // the MMA thread may overwrite this accumulator
+      }
+      if (o < n_out) {
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::kCols; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = acc[c0 + q];
+          ovf |= epilogue16(v, epi, (size_t)o * COUT, col0 + c0, out_hi, out_lo, out_f32);
+        }
+      }
+    }
+    if (ovf && overflow) atomicOr(overflow, 1);
+  } else if (warp < Cfg::kMmaWarp) {
     // ===================== gather producers =====================
-    const int group = warp >> 2, wq = warp & 3;
+    const int gw = warp - Cfg::kGatherWarp0;
+    const int group = gw >> 1, wq = gw & 1;                     // two warps per group, 64 rows each
     const int g = lane >> 3, c = lane & 7;
     const bool issues_tma = (wq == 0 && lane == 0);
-    const int ptid = threadIdx.x;      // 0 .. 511
+    const int ptid = threadIdx.x - 32 * Cfg::kGatherWarp0;      // 0 .. 64 * kGroups - 1
     const int c_in_pad = (c_in + 15) & ~15;
+    uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * kOsTileM;
       const unsigned int mask = tile_mask[tile];
@@ -197,8 +247,8 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       const int n_slots = n_off * n_kb;
 
       // stage nbr[k][row0 .. row0+127] for the active offsets (one global round trip per tile)
-      asm volatile("bar.sync 1, %0;" ::"r"(128 * Cfg::kGroups) : "memory");   // previous tile's readers are done
-      for (int idx = ptid; idx < n_off * kOsTileM; idx += 128 * Cfg::kGroups) {
+      asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");   // previous tile's readers are done
+      for (int idx = ptid; idx < n_off * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {
         const int n = idx >> 7, r = idx & 127;
         unsigned int m = mask;
         for (int t = n; t > 0; --t) m &= m - 1;
@@ -206,7 +256,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         if (r == 0) koff_s[n] = k;
         nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)k * out_cap + row0 + r) : -1;
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(128 * Cfg::kGroups) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
 
       for (int j = (int)((group + Cfg::kGroups - (it0 % Cfg::kGroups)) % Cfg::kGroups); j < n_slots; j += Cfg::kGroups) {
         const int n = j / n_kb, kb = j - n * n_kb;
@@ -222,9 +272,9 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                        full_bar(s));
         }
         if (ch < c_in_pad) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int row = wq * 32 + 4 * q + g;
+#pragma unroll 4
+          for (int q = 0; q < 16; ++q) {
+            const int row = wq * 64 + 4 * q + g;
             const int src = nbr_s[n * kOsTileM + row];
             const bool live = src >= 0 && ch < c_in;
             const size_t off = live ? (size_t)src * c_in + ch : 0;
@@ -239,82 +289,42 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       }
       it0 += (uint32_t)n_slots;
     }
-  } else if (warp == Cfg::kMmaWarp) {
+  } else {
     // ===================== MMA issuer (one elected lane) =====================
-    constexpr uint32_t idesc2 = umma_idesc_f16(kOsTileM, 2 * COUT);   // A_hi x [B_hi | B_lo]
-    constexpr uint32_t idesc1 = umma_idesc_f16(kOsTileM, COUT);       // A_lo x B_hi
+    // Every slot (offset, 64-channel slice) is accumulated from zero in its own TMEM buffer: the chain of
+    // truncating tensor-core accumulations is <= 12 MMAs long, everything beyond is summed by the accumulator warps.
+    constexpr uint32_t idesc = umma_idesc_f16(kOsTileM, COUT);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const unsigned int mask = tile_mask[tile];
-      if (mask == 0) continue;
-      const int n_slots = __popc(mask) * n_kb;
-      const uint32_t buf = tile_it & 1u;
-      D3B_WAIT(acc_empty(buf), ((tile_it >> 1) & 1u) ^ 1u, 2);
-      tc_fence_after();
-      const uint32_t d_addr = tmem_d + buf * Cfg::kAccCols;
-      uint32_t accumulate = 0;
+      const int n_slots = __popc(tile_mask[tile]) * n_kb;
       for (int j = 0; j < n_slots; ++j, ++it) {
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
+        const uint32_t buf = it & 1u;
         const int kb = j % n_kb;
         const int n_ks = min(kOsKc / 16, (c_in - kb * kOsKc + 15) / 16);
+        D3B_WAIT(acc_empty(buf), ((it >> 1) & 1u) ^ 1u, 2);
         D3B_WAIT(full_bar(s), ph, 3);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
           const uint32_t a_lo = a_hi + kOsABytes;
-          const uint32_t b = a_lo + kOsABytes;
+          const uint32_t b_hi = a_lo + kOsABytes;
+          const uint32_t b_lo = b_hi + COUT * 128;
+          const uint32_t d_addr = tmem_d + buf * Cfg::kAccCols;
           for (int ks = 0; ks < n_ks; ++ks) {
             const uint32_t adv = ks * 32;   // 16 f16 = 32 bytes along K inside the swizzle row
-            tc_mma_f16(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b + adv), idesc2, accumulate);
-            tc_mma_f16(d_addr, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b + adv), idesc1, 1u);
-            accumulate = 1u;
+            // small terms first, the dominant hi.hi product last
+            tc_mma_f16(d_addr, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, ks > 0 ? 1u : 0u);
+            tc_mma_f16(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
+            tc_mma_f16(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
           }
-          tc_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+          tc_commit(empty_bar(s));      // frees the operand stage when these MMAs have read it
+          tc_commit(acc_full(buf));     // ... and hands the partial sums to the accumulator warps
         }
         __syncwarp();
-        accumulate = 1u;
-      }
-      if (lane == 0) tc_commit(acc_full(buf));
-      __syncwarp();
-      ++tile_it;
-    }
-  } else {
-    // ===================== epilogue warps: TMEM -> fused bias/BN/residual/ReLU -> f16 planes =====================
-    const int quad = warp & 3;
-    bool ovf = false;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const bool any = tile_mask[tile] != 0u;
-      const int o = tile * kOsTileM + quad * 32 + lane;
-      const uint32_t buf = tile_it & 1u;
-      if (any) {
-        D3B_WAIT(acc_full(buf), (tile_it >> 1) & 1u, 4);
-        tc_fence_after();
-      }
-      const uint32_t t0 = tmem_d + buf * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
-        float v[16];
-        if (any) {
-          uint32_t r1[16], r2[16];
-          tc_ld16_nowait(t0 + c0, r1);
-          tc_ld16_nowait(t0 + COUT + c0, r2);
-          tc_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r1[q]) + __uint_as_float(r2[q]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = 0.f;
-        }
-        if (o < n_out) ovf |= epilogue16(v, epi, (size_t)o * COUT, c0, out_hi, out_lo, out_f32);
-      }
-      if (any) {
-        tc_fence_before();
-        mbar_arrive(acc_empty(buf));
-        ++tile_it;
       }
     }
-    if (ovf && overflow) atomicOr(overflow, 1);
   }
 
   tc_fence_before();

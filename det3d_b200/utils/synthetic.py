@@ -158,6 +158,9 @@ def calibrate_demo_weights_(model, cfg, clouds, seed=0, pass_fraction=0.03, box_
         c = mean.shape[0]
         bn.running_mean.copy_(mean + 0.1 * var.sqrt() * torch.randn(c, generator=g).to(dev))
         bn.running_var.copy_(var * (0.8 + 0.45 * torch.rand(c, generator=g).to(dev)))
+        if not getattr(bn, "_d3b_gamma_scaled", False):     # trained gammas sit below 1: keeps the activations' tails within ~10
+            bn.weight.mul_(0.6)
+            bn._d3b_gamma_scaled = True
 
     for m in model.modules():
         if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
@@ -189,7 +192,10 @@ def calibrate_demo_weights_(model, cfg, clouds, seed=0, pass_fraction=0.03, box_
             thr = float(cfg.test_cfg["score_threshold"])
             for task in model.bbox_head.tasks:
                 logit = task.conv_cls(x)
-                task.conv_cls.weight.div_(logit.std().clamp_min(1e-6))
+                # realistic logit range: the 99.99 % quantile of |logit - mean| lands on 6 (sigmoid(6) = 0.9975)
+                dev_abs = (logit.float() - logit.float().mean()).abs().reshape(-1)
+                spread = dev_abs.kthvalue(max(1, int(dev_abs.numel() * 0.9999)))[0]
+                task.conv_cls.weight.mul_(6.0 / spread.clamp_min(1e-6))
                 task.conv_cls.bias.zero_()
                 logit = task.conv_cls(x)
                 best = logit.float().amax(dim=1).reshape(-1) if logit.shape[1] > 1 else logit.float().reshape(-1)
@@ -200,6 +206,10 @@ def calibrate_demo_weights_(model, cfg, clouds, seed=0, pass_fraction=0.03, box_
                 box = task.conv_box(x)
                 task.conv_box.weight.mul_(box_std / box.std().clamp_min(1e-6))
                 task.conv_box.bias.zero_()
+                if getattr(task, "use_dir", False):
+                    d = task.conv_dir(x).float().abs().reshape(-1)
+                    task.conv_dir.weight.mul_(6.0 / d.kthvalue(max(1, int(d.numel() * 0.9999)))[0].clamp_min(1e-6))
+                    task.conv_dir.bias.zero_()
     finally:
         torch.backends.cudnn.allow_tf32 = prev
         for h in hooks:
