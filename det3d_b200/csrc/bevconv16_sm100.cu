@@ -17,13 +17,16 @@
 //    the SAME staged patch with the UMMA descriptor start advanced by ky * 1024 bytes: one patch load per (kx, 64
 //    channels) serves three (ky, kx) offsets.
 //  * FP16x3: per k-step three MMAs (A_lo.B_hi, A_hi.B_lo, A_hi.B_hi) with fp32 accumulation in TMEM -- but only
-//    across ONE weight stage (12 MMAs): the tensor core truncates on every accumulation, and chaining all 72+ k-steps of a
-//    3x3x128 reduction into one accumulator shrank the outputs by ~4e-6 per layer (measured: error proportional to chain
-//    length), which 20 layers turn into > 1e-4.  Each stage therefore starts from zero in its own TMEM buffer pair (two
-//    pairs: stage s+1 accumulates while stage s is drained) and eight accumulator warps add the stages in fp32 registers
-//    with round-to-nearest, then apply bias / BN / ReLU and write the f16 planes.
-//  * Warp roles: 1 TMA warp, 1 MMA warp, 8 accumulator warps (one per TMEM quadrant and half); A ring of 2 stages
-//    (4 patches each), B ring of 2..4 stages, all mbarrier-driven; persistent grid (143 tiles at 200 x 176).
+//    across ONE A stage (the three kernel rows of a (kx, 64-channel slice)): the tensor core truncates on every
+//    accumulation, and chaining all 216 MMAs of a 3x3x128 reduction into one accumulator shrank the outputs by ~4e-6
+//    per layer (measured: error proportional to chain length), which 20 layers turn into > 1e-4.  A half's accumulator
+//    therefore lives for one A stage (36 accumulations) in one of two TMEM buffers; eight accumulator warps add the
+//    finished buffer into fp32 registers with round-to-nearest while the next A stage fills the other one, and at the
+//    end of the tile apply bias / BN / ReLU and write the f16 planes.
+//  * Warp roles: 1 TMA warp, 2 MMA warps (one issuing thread per half: a single thread issues one tcgen05.mma per
+//    ~65 cycles -- clock-stamp trace -- which equals the pipe time of M128 x N128 x K16), 8 accumulator warps (one per
+//    TMEM quadrant and half); A ring of 2 stages (4 patches each), B ring of 2..4 stages, all mbarrier-driven;
+//    persistent grid (143 tiles at 200 x 176).
 //  * stride 2 (RPN down-sampling blocks): the box is loaded with elementStrides = 2, one load per (ky, kx).
 //  * groups: several weight blocks over the same input in one launch -- C_out = 256 as two N = 128 passes, and
 //    ConvTranspose2d(k = s, stride = s) as s*s 1x1 convolutions whose epilogues write pixel (y*s + dy, x*s + dx)
@@ -48,8 +51,10 @@ struct BvEpi {          // same fields as spconv16_sm100.cu (kept local: the two
 constexpr int kBvTileY = 16, kBvTileX = 16;     // output pixels per tile
 constexpr int kBvHalfX = 8;                     // one M = 128 half = 16 rows x 8 columns
 constexpr int kBvKc = 64;                       // channels per stage (128 bytes of f16)
-constexpr int kBvTmaWarp = 0, kBvMmaWarp = 1, kBvEpiWarp0 = 2;
-constexpr int kBvThreads = 32 * (kBvEpiWarp0 + 8);   // 320
+// warp roles: TMA producer, one MMA-issuing warp per half (a single thread issues ~one tcgen05.mma per 65 cycles --
+// measured -- which is exactly the pipe time of an M128 x N128 x K16 MMA: two issuers keep the pipe fed), 8 accumulator warps
+constexpr int kBvTmaWarp = 0, kBvMmaWarp = 1, kBvEpiWarp0 = 3;
+constexpr int kBvThreads = 32 * (kBvEpiWarp0 + 8);   // 352
 constexpr int kBvAStages = 2;
 
 template <int KS, int STRIDE, int COUT>
@@ -59,8 +64,8 @@ struct BvCfg {
   static constexpr int kAStageBytes = 4 * kPatchBytes;                                // {half 0, half 1} x {hi, lo}
   static constexpr int kBBytes = 2 * COUT * 128;                                      // [B_hi rows | B_lo rows]
   static constexpr int kBStages = COUT >= 128 ? 2 : 4;
-  static constexpr int kAccCols = COUT;                                               // one (stage, half) accumulator
-  static constexpr int kTmemCols = 4 * kAccCols;                                      // {2 buffers} x {2 halves}: 128 .. 512
+  static constexpr int kAccCols = COUT;                                               // one accumulator
+  static constexpr int kTmemCols = 4 * kAccCols;                                      // {2 halves} x {2 buffers}: 128 .. 512
   static constexpr int kSmemBytes = kBvAStages * kAStageBytes + kBStages * kBBytes + 1024 + 256;
   // with stride 1 one A stage serves the KS kernel rows of a (kx, kb); with stride 2 every (ky, kx) has its own
   static constexpr int kRowsPerAStage = STRIDE == 1 ? KS : 1;
@@ -97,27 +102,29 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   auto a_empty = [&](int s) { return bar_base + 8u * (kBvAStages + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * kBvAStages + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * kBvAStages + Cfg::kBStages + s); };
-  auto acc_full = [&](uint32_t b) { return bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages + b); };
-  auto acc_empty = [&](uint32_t b) { return bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kBvAStages + 2 * Cfg::kBStages + 4));
+  // accumulator hand-off, per (half, buffer): index half * 2 + buffer
+  auto acc_full = [&](uint32_t hb) { return bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages + hb); };
+  auto acc_empty = [&](uint32_t hb) { return bar_base + 8u * (2 * kBvAStages + 2 * Cfg::kBStages + 4 + hb); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kBvAStages + 2 * Cfg::kBStages + 8));
 
+  D3B_CTA_MARK(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_group = g.batch * g.tiles_y * g.tiles_x;
   const int n_tiles = tiles_per_group * g.groups;
   const int k_vol = KS * KS;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBvAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (uint32_t b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);       // tcgen05.commit of one weight stage's MMAs
-      mbar_init(acc_empty(b), 256);    // the eight accumulator warps have read that stage's partial sums
+    for (int s = 0; s < kBvAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 2); }      // freed by both MMA threads
+    for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
+    for (uint32_t hb = 0; hb < 4; ++hb) {
+      mbar_init(acc_full(hb), 1);      // tcgen05.commit of the half's MMAs of one A stage
+      mbar_init(acc_empty(hb), 128);   // the half's four accumulator warps have read those partial sums
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
   }
-  if (warp == kBvMmaWarp) {
+  if (warp == kBvMmaWarp) {     // (the first MMA warp owns the TMEM allocation)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -151,6 +158,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
             for (int ky0 = 0; ky0 < KS; ky0 += Cfg::kRowsPerAStage) {
               // ---- A stage: {half 0, half 1} x {hi, lo} patches ----
               const int sa = a_it % kBvAStages;
+              D3B_STAMP(0, a_it);
               D3B_WAIT(a_empty(sa), ((a_it / kBvAStages) & 1u) ^ 1u, 1);
               mbar_arrive_expect_tx(a_full(sa), Cfg::kAStageBytes);
               const uint32_t dst = a_base + sa * Cfg::kAStageBytes;
@@ -161,15 +169,18 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
                 tma_load_4d(dst + (2 * half) * Cfg::kPatchBytes, &tm_hi, kb * kBvKc, cx, cy, b, a_full(sa));
                 tma_load_4d(dst + (2 * half + 1) * Cfg::kPatchBytes, &tm_lo, kb * kBvKc, cx, cy, b, a_full(sa));
               }
+              D3B_STAMP(1, a_it);
               ++a_it;
               // ---- B stages: one per kernel row served by this A stage ----
               for (int r = 0; r < Cfg::kRowsPerAStage; ++r) {
                 const int ky = ky0 + r;
                 const int sb = b_it % Cfg::kBStages;
+                D3B_STAMP(2, b_it);
                 D3B_WAIT(b_empty(sb), ((b_it / Cfg::kBStages) & 1u) ^ 1u, 2);
                 mbar_arrive_expect_tx(b_full(sb), Cfg::kBBytes);
                 tma_bulk_g2s(b_base + sb * Cfg::kBBytes,
                              wgrp + ((size_t)(ky * KS + kx) * g.n_kb + kb) * (Cfg::kBBytes / 2), Cfg::kBBytes, b_full(sb));
+                D3B_STAMP(3, b_it);
                 ++b_it;
               }
             }
@@ -177,12 +188,13 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == kBvMmaWarp) {
-    // ===================== MMA issuer (one elected lane) =====================
-    // Every weight stage (one (ky, kx, 64-channel slice), both halves) is accumulated from zero in its own pair of TMEM
-    // buffers: the chain of truncating tensor-core accumulations is 12 MMAs long, the stages are summed by the
-    // accumulator warps in fp32 registers with round-to-nearest.
+  } else if (warp < kBvEpiWarp0) {
+    // ===================== MMA issuers: warp 1 -> half 0, warp 2 -> half 1 (one elected lane each) =====================
+    // The half's accumulator lives for one A stage (the KS kernel rows of a (kx, 64-channel slice): 36 chained
+    // accumulations -- the tensor core truncates on each, see the header) in one of two TMEM buffers; the accumulator warps
+    // add it into fp32 registers while the next A stage fills the other buffer.
     constexpr uint32_t idesc = umma_idesc_f16(128, COUT);
+    const int half = warp - kBvMmaWarp;
     uint32_t a_it = 0, b_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < g.n_kb; ++kb) {
@@ -190,38 +202,42 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         for (int kx = 0; kx < KS; ++kx) {
           for (int ky0 = 0; ky0 < KS; ky0 += Cfg::kRowsPerAStage) {
             const int sa = a_it % kBvAStages;
+            const uint32_t hb = half * 2 + (a_it & 1u);
+            if (lane == 0 && half == 0) D3B_STAMP(4, a_it);
+            D3B_WAIT(acc_empty(hb), ((a_it >> 1) & 1u) ^ 1u, 3);        // this buffer's previous sums have been read out
             D3B_WAIT(a_full(sa), (a_it / kBvAStages) & 1u, 4);
+            if (lane == 0 && half == 0) D3B_STAMP(5, a_it);
+            const uint32_t d_addr = tmem_d + hb * Cfg::kAccCols;
             for (int r = 0; r < Cfg::kRowsPerAStage; ++r, ++b_it) {
               const int sb = b_it % Cfg::kBStages;
-              const uint32_t buf = b_it & 1u;
-              D3B_WAIT(acc_empty(buf), ((b_it >> 1) & 1u) ^ 1u, 3);
               D3B_WAIT(b_full(sb), (b_it / Cfg::kBStages) & 1u, 5);
+              if (lane == 0 && half == 0) D3B_STAMP(6, b_it);
               tc_fence_after();
-              if (lane == 0) {
+              {
+                // warp-uniform instruction stream (descriptor arithmetic stays in uniform registers); lane 0 issues
+                const uint32_t issue = lane == 0 ? 1u : 0u;
                 const uint32_t b_hi = b_base + sb * Cfg::kBBytes;
-                const uint32_t b_lo = b_hi + COUT * 128;
                 // stride 1: kernel row r of the staged patch = the same bytes 8 rows (1024 B) further down
                 const uint32_t row_adv = STRIDE == 1 ? (uint32_t)(ky0 + r) * 1024u : 0u;
+                const uint32_t ah = a_base + sa * Cfg::kAStageBytes + (2 * half) * Cfg::kPatchBytes + row_adv;
+                const uint64_t da_hi = umma_desc_sw128(ah), da_lo = umma_desc_sw128(ah + Cfg::kPatchBytes);
+                const uint64_t db_hi = umma_desc_sw128(b_hi), db_lo = umma_desc_sw128(b_hi + COUT * 128);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                  const uint32_t ah = a_base + sa * Cfg::kAStageBytes + (2 * half) * Cfg::kPatchBytes + row_adv;
-                  const uint32_t al = ah + Cfg::kPatchBytes;
-                  const uint32_t d_addr = tmem_d + (buf * 2 + half) * Cfg::kAccCols;
-                  for (int ks = 0; ks < n_ks; ++ks) {
-                    const uint32_t adv = ks * 32;
+                for (int ks = 0; ks < kBvKc / 16; ++ks) {
+                  if (ks < n_ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);     // 32 bytes along K = 2 descriptor address units
                     // small terms first, the dominant hi.hi product last
-                    tc_mma_f16(d_addr, umma_desc_sw128(al + adv), umma_desc_sw128(b_hi + adv), idesc, ks > 0 ? 1u : 0u);
-                    tc_mma_f16(d_addr, umma_desc_sw128(ah + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
-                    tc_mma_f16(d_addr, umma_desc_sw128(ah + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
+                    tc_mma_f16_if(issue, d_addr, da_lo + adv, db_hi + adv, idesc, (r | ks) ? 1u : 0u);
+                    tc_mma_f16_if(issue, d_addr, da_hi + adv, db_lo + adv, idesc, 1u);
+                    tc_mma_f16_if(issue, d_addr, da_hi + adv, db_hi + adv, idesc, 1u);
                   }
                 }
-                tc_commit(b_empty(sb));
-                tc_commit(acc_full(buf));
+                tc_commit_if(issue, b_empty(sb));
+                if (lane == 0 && half == 0) D3B_STAMP(7, b_it);
               }
-              __syncwarp();
             }
-            if (lane == 0) tc_commit(a_empty(sa));
-            __syncwarp();
+            tc_commit_if(lane == 0 ? 1u : 0u, a_empty(sa));
+            tc_commit_if(lane == 0 ? 1u : 0u, acc_full(hb));
             ++a_it;
           }
         }
@@ -230,12 +246,12 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   } else {
     // ===================== accumulator warps: TMEM partial sums -> fp32 registers -> bias / BN / ReLU -> NHWC planes =====
     const int ew = warp - kBvEpiWarp0;          // 0..7
-    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read (warps 3..6 and 7..10: 3,0,1,2)
     const int half = ew >> 2;
     const int m = quad * 32 + lane;             // pixel of the half: row m / 8, column m % 8
-    const int n_stages = g.n_kb * k_vol;        // weight stages per tile
+    const int n_groups = g.n_kb * k_vol / Cfg::kRowsPerAStage;      // accumulator groups (A stages) per tile
     bool ovf = false;
-    uint32_t b_it = 0;
+    uint32_t a_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       int grp, b, y0, x0;
       decode(tile, grp, b, y0, x0);
@@ -243,20 +259,30 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
 #pragma unroll
       for (int q = 0; q < COUT; ++q) acc[q] = 0.f;
 #pragma unroll 1
-      for (int st = 0; st < n_stages; ++st, ++b_it) {
-        const uint32_t buf = b_it & 1u;
-        D3B_WAIT(acc_full(buf), (b_it >> 1) & 1u, 6);
+      for (int gi = 0; gi < n_groups; ++gi, ++a_it) {
+        const uint32_t hb = half * 2 + (a_it & 1u);
+        if (ew == 0 && lane == 0) D3B_STAMP(8, a_it);
+        D3B_WAIT(acc_full(hb), (a_it >> 1) & 1u, 6);
+        if (ew == 0 && lane == 0) D3B_STAMP(9, a_it);
         tc_fence_after();
-        const uint32_t t0 = tmem_d + (buf * 2 + half) * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t0 = tmem_d + hb * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16);
+        const int kb_g = gi * Cfg::kRowsPerAStage / k_vol;
+        const int n_chain = 3 * Cfg::kRowsPerAStage * min(kBvKc / 16, (g.c_in - kb_g * kBvKc + 15) / 16);   // MMAs chained into the buffer
+        const float f_fix = 1.f + (float)n_chain * kTruncLossPerMma;
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 16) {
-          uint32_t r[16];
-          tc_ld16(t0 + c0, r);
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t r0[16], r1[16];
+          tc_ld16_nowait(t0 + c0, r0);
+          tc_ld16_nowait(t0 + c0 + 16, r1);
+          tc_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) acc[c0 + q] += __uint_as_float(r[q]);
+          for (int q = 0; q < 16; ++q) acc[c0 + q] = fmaf(__uint_as_float(r0[q]), f_fix, acc[c0 + q]);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + 16 + q] = fmaf(__uint_as_float(r1[q]), f_fix, acc[c0 + 16 + q]);
         }
         tc_fence_before();
-        mbar_arrive(acc_empty(buf));
+        mbar_arrive(acc_empty(hb));
+        if (ew == 0 && lane == 0) D3B_STAMP(10, a_it);
       }
       const int y = y0 + (m >> 3), x = x0 + half * kBvHalfX + (m & 7);
       if (!(y < g.h_out && x < g.w_out)) continue;
@@ -319,6 +345,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  D3B_CTA_MARK(1);
   if (warp == kBvMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
@@ -442,6 +469,17 @@ extern "C" int d3b_debug_fault_bevconv16(unsigned int* host8) {
   cudaError_t e = cudaMemcpyFromSymbol(host8, d3b::g_d3b_fault, 32);
   unsigned int zeros[8] = {0};
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(d3b::g_d3b_fault, zeros, 32);
+  return (int)e;
+}
+extern "C" int d3b_debug_cta_ns_bevconv16(unsigned long long* host512) {
+  return (int)cudaMemcpyFromSymbol(host512, d3b::g_d3b_cta_ns, sizeof(unsigned long long) * 512);
+}
+extern "C" int d3b_debug_trace_bevconv16(long long* host, int clear) {
+  cudaError_t e = cudaMemcpyFromSymbol(host, d3b::g_d3b_trace, sizeof(long long) * 16 * 512);
+  if (e == cudaSuccess && clear) {
+    static long long zeros[16 * 512];
+    e = cudaMemcpyToSymbol(d3b::g_d3b_trace, zeros, sizeof(zeros));
+  }
   return (int)e;
 }
 #endif

@@ -631,19 +631,48 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
   extern __shared__ unsigned long long remv[];
   __shared__ unsigned long long diag[kNmsBlock];
   __shared__ unsigned long long kept_word;
-  __shared__ int kept_total;
+  __shared__ int kept_total, kept_base;
   const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int nb = (n + kNmsBlock - 1) / kNmsBlock;
   unsigned long long* smask = remv + col_blocks_alloc;      // [n][nb] when stage_mask
   for (int j = threadIdx.x; j < nb; j += blockDim.x) remv[j] = 0ULL;
   if (threadIdx.x == 0) kept_total = 0;
   if (stage_mask) {
-    for (int e = threadIdx.x; e < n * nb; e += blockDim.x) {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < n * nb; e += blockDim.x) {      // independent 8-byte loads, four in flight per thread
       const int i = e / nb, j = e - i * nb;
-      smask[e] = j >= (i >> 6) ? mask[(size_t)i * col_blocks_alloc + j] : 0ULL;
+      smask[e] = j >= (i >> 6) ? __ldg(mask + (size_t)i * col_blocks_alloc + j) : 0ULL;
     }
   }
   __syncthreads();
+  if (stage_mask) {
+    // The detector's operating point (N <= ~1400, mask staged in shared memory): ONE warp walks the kept rows only.
+    // Lane j holds remv[j]; per column block the not-yet-suppressed candidates are the zero bits of its word, the next
+    // kept row is found with ffs, its mask row (nb <= 22 words, one per lane) is ORed in -- ~(kept + nb) short iterations
+    // instead of four block-wide barriers and a 64-step serial scan per block.
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      unsigned long long rem = 0ULL;
+      int total = 0;
+      for (int b = 0; b < nb && total < max_keep; ++b) {
+        const int in_block = min(n - b * kNmsBlock, kNmsBlock);
+        const unsigned long long valid = in_block >= 64 ? ~0ULL : ((1ULL << in_block) - 1ULL);
+        unsigned long long avail = ~__shfl_sync(0xffffffffu, rem, b) & valid;
+        while (avail != 0ULL && total < max_keep) {
+          const int i = __ffsll((long long)avail) - 1;
+          const int row = b * kNmsBlock + i;
+          if (lane == 0) keep_idx[total] = (long long)row;
+          ++total;
+          const unsigned long long r = lane < nb ? smask[(size_t)row * nb + lane] : 0ULL;
+          rem |= r;
+          avail &= ~__shfl_sync(0xffffffffu, r, b);          // suppressed inside this block
+          avail &= ~((2ULL << i) - 1ULL);                     // row i itself and everything before it is decided
+        }
+      }
+      if (lane == 0) *keep_count = total;
+    }
+    return;
+  }
   for (int b = 0; b < nb; ++b) {
     const int in_block = min(n - b * kNmsBlock, kNmsBlock);
     if ((int)threadIdx.x < in_block) {
@@ -652,9 +681,10 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      // serial resolve of the 64 rows of this block: ALU-only chain (the diag words are fetched eight at a time, the
+      // keep list is written afterwards, in parallel, from the `kept` bits)
       unsigned long long cur = remv[b], kept = 0ULL;
       int total = kept_total;
-      // the diag loads do not depend on `cur`: fetch them eight at a time so the serial chain is ALU-only
       for (int i0 = 0; i0 < in_block && total < max_keep; i0 += 8) {
         unsigned long long d8[8];
 #pragma unroll
@@ -665,26 +695,30 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
           if (i < in_block && total < max_keep && !((cur >> i) & 1ULL)) {
             kept |= 1ULL << i;
             cur |= d8[u];
-            keep_idx[total++] = (long long)b * kNmsBlock + i;
+            ++total;
           }
         }
       }
       kept_word = kept;
+      kept_base = kept_total;
       kept_total = total;
     }
     __syncthreads();
     const unsigned long long kept = kept_word;
+    if (threadIdx.x < kNmsBlock && ((kept >> threadIdx.x) & 1ULL))       // keep list: rank among the kept rows of the block
+      keep_idx[kept_base + __popcll(kept & ((1ULL << threadIdx.x) - 1ULL))] = (long long)b * kNmsBlock + threadIdx.x;
     if (kept_total >= max_keep) break;
     if (kept != 0ULL && stage_mask) {
-      // staged mask (the detector's operating point, nb <= 22): one (kept row, column block) entry per thread instead
-      // of a thread per column block walking up to 64 rows with dependent shared-memory loads
-      const int ncol = nb - (b + 1);
-      for (int e = threadIdx.x; e < kNmsBlock * ncol; e += blockDim.x) {
-        const int i = e / ncol, j = b + 1 + (e - i * ncol);
-        if ((kept >> i) & 1ULL) {
-          const unsigned long long v = smask[(size_t)(b * kNmsBlock + i) * nb + j];
-          if (v != 0ULL) atomicOr(&remv[j], v);
-        }
+      // staged mask (the detector's operating point, nb <= 22): one warp per later column block ORs the kept rows' words
+      // (two rows per lane, warp reduction) -- no atomics, no dependent shared-memory chain
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+      for (int j = b + 1 + warp; j < nb; j += n_warps) {
+        unsigned long long v = 0ULL;
+        if ((kept >> lane) & 1ULL) v |= smask[(size_t)(b * kNmsBlock + lane) * nb + j];
+        if ((kept >> (lane + 32)) & 1ULL) v |= smask[(size_t)(b * kNmsBlock + lane + 32) * nb + j];
+        unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v);
+        unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
+        if (lane == 0) remv[j] |= ((unsigned long long)hi << 32) | lo;
       }
     } else if (kept != 0ULL) {
       for (int j = b + 1 + threadIdx.x; j < nb; j += blockDim.x) {

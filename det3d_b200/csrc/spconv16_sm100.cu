@@ -60,8 +60,15 @@ struct OsCfg {
   static constexpr int kGroupThreads = 64;                 // (few threads: the register file goes to the accumulators)
   static constexpr int kMmaWarp = kEpiWarps + 2 * kGroups; // TMEM alloc + MMA issue
   static constexpr int kThreads = 32 * (kMmaWarp + 1);     // 416 (C_out 16/32), 544 (64), 480 (128)
-  static constexpr int kAccCols = COUT < 32 ? 32 : COUT;   // one per-slot accumulator
-  static constexpr int kTmemCols = 2 * kAccCols;           // two of them: slot j+1 accumulates while slot j is drained
+  // Accumulators.  Per k-step TWO MMAs: A_hi x [B_hi | B_lo] (N = 2 C_out: the hi.hi and hi.lo products side by side)
+  // and A_lo x B_hi (N = C_out, onto the hi.hi columns) -- a single thread issues only ~one tcgen05.mma per 65..90
+  // cycles (clock-stamp trace), three N = C_out MMAs per k-step made the issue rate the bottleneck.
+  static constexpr int kBufCols = 2 * COUT;                // [hi.hi + lo.hi | hi.lo]
+  static constexpr int kTmemCols = 2 * kBufCols;           // two buffers: group g+1 accumulates while group g is drained
+  // An accumulator buffer lives for kFlush slots (offsets), then the accumulator warps add it into fp32 registers: the
+  // chain of truncating tensor-core accumulations stays <= kFlush * 8 MMAs, and the TMEM read (the slow direction)
+  // is amortised over kFlush slots.
+  static constexpr int kFlush = 3;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 32 * kOsTileM * 4;
 };
 
@@ -165,6 +172,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   int* koff_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 128);   // [32] active offsets
   int* nbr_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);    // [32][128] neighbour rows
 
+  D3B_CTA_MARK(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = min(*n_out_p, out_cap);
   const int n_tiles = (n_out + kOsTileM - 1) / kOsTileM;
@@ -205,20 +213,32 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       float acc[Cfg::kCols];
 #pragma unroll
       for (int q = 0; q < Cfg::kCols; ++q) acc[q] = 0.f;
-      for (int j = 0; j < n_slots; ++j, ++it) {
+      const int n_groups = (n_slots + Cfg::kFlush - 1) / Cfg::kFlush;
+      for (int gi = 0; gi < n_groups; ++gi, ++it) {
         const uint32_t buf = it & 1u;
+        if (warp == 0 && lane == 0) D3B_STAMP(8, it);
         D3B_WAIT(acc_full(buf), (it >> 1) & 1u, 4);
+        if (warp == 0 && lane == 0) D3B_STAMP(9, it);
         tc_fence_after();
-        const uint32_t t0 = tmem_d + buf * Cfg::kAccCols + ((uint32_t)(quad * 32) << 16) + col0;
+        const uint32_t t0 = tmem_d + buf * Cfg::kBufCols + ((uint32_t)(quad * 32) << 16) + col0;
+        int n_ks_sum = 0;                               // k-steps chained into this buffer
+        for (int j = gi * Cfg::kFlush; j < min((gi + 1) * Cfg::kFlush, n_slots); ++j)
+          n_ks_sum += min(kOsKc / 16, (c_in - (j % n_kb) * kOsKc + 15) / 16);
+        const float f_hh = 1.f + 2.f * (float)n_ks_sum * kTruncLossPerMma;     // two MMAs per k-step land on these columns
+        const float f_hl = 1.f + (float)n_ks_sum * kTruncLossPerMma;
 #pragma unroll
         for (int c0 = 0; c0 < Cfg::kCols; c0 += 16) {
-          uint32_t r[16];
-          tc_ld16(t0 + c0, r);
+          uint32_t r0[16], r1[16];
+          tc_ld16_nowait(t0 + c0, r0);                 // hi.hi + lo.hi
+          tc_ld16_nowait(t0 + COUT + c0, r1);          // hi.lo
+          tc_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) acc[c0 + q] += __uint_as_float(r[q]);
+          for (int q = 0; q < 16; ++q)
+            acc[c0 + q] += fmaf(__uint_as_float(r0[q]), f_hh, __uint_as_float(r1[q]) * f_hl);
         }
         tc_fence_before();
-        mbar_arrive(acc_empty(buf));               // the MMA thread may overwrite this accumulator
+        mbar_arrive(acc_empty(buf));               // the MMA thread may overwrite this buffer
+        if (warp == 0 && lane == 0) D3B_STAMP(10, it);
       }
       if (o < n_out) {
 #pragma unroll
@@ -248,13 +268,16 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
       // stage nbr[k][row0 .. row0+127] for the active offsets (one global round trip per tile)
       asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");   // previous tile's readers are done
-      for (int idx = ptid; idx < n_off * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {
-        const int n = idx >> 7, r = idx & 127;
+      if (ptid < 32) {                                    // n-th active offset of the tile
         unsigned int m = mask;
-        for (int t = n; t > 0; --t) m &= m - 1;
-        const int k = __ffs(m) - 1;
-        if (r == 0) koff_s[n] = k;
-        nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)k * out_cap + row0 + r) : -1;
+        for (int t = ptid; t > 0; --t) m &= m - 1;
+        if (ptid < n_off) koff_s[ptid] = __ffs(m) - 1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
+#pragma unroll 8
+      for (int idx = ptid; idx < n_off * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {   // independent loads
+        const int r = idx & 127;
+        nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)koff_s[idx >> 7] * out_cap + row0 + r) : -1;
       }
       asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
 
@@ -264,7 +287,9 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         const uint32_t it = it0 + (uint32_t)j;
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
+        if (issues_tma) D3B_STAMP(0, it);
         D3B_WAIT(empty_bar(s), ph ^ 1u, 1);
+        if (issues_tma) D3B_STAMP(1, it);
         const uint32_t stage = smem_base + s * Cfg::kStageBytes;
         if (issues_tma) {
           mbar_arrive_expect_tx(full_bar(s), Cfg::kBBytes);
@@ -272,18 +297,28 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                        full_bar(s));
         }
         if (ch < c_in_pad) {
-#pragma unroll 4
-          for (int q = 0; q < 16; ++q) {
-            const int row = wq * 64 + 4 * q + g;
-            const int src = nbr_s[n * kOsTileM + row];
-            const bool live = src >= 0 && ch < c_in;
-            const size_t off = live ? (size_t)src * c_in + ch : 0;
-            const uint32_t dst = stage + sw128_offset(row, c);
-            cp_async16(dst, in_hi + off, live ? 16u : 0u);
-            cp_async16(dst + kOsABytes, in_lo + off, live ? 16u : 0u);
+          // this thread: 16 consecutive rows (indices fetched as four 16-byte shared-memory loads), one 16-byte chunk
+          const int row_base = wq * 64 + g * 16;
+          const int4* idx4 = reinterpret_cast<const int4*>(nbr_s + n * kOsTileM + row_base);
+          const bool col_live = ch < c_in;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int4 iv = idx4[q4];
+            const int srcs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = row_base + q4 * 4 + u;
+              const bool live = srcs[u] >= 0 && col_live;
+              const size_t off = live ? (size_t)srcs[u] * c_in + ch : 0;
+              const uint32_t dst = stage + sw128_offset(row, c);
+              cp_async16(dst, in_hi + off, live ? 16u : 0u);
+              cp_async16(dst + kOsABytes, in_lo + off, live ? 16u : 0u);
+            }
           }
         }
+        if (issues_tma) D3B_STAMP(2, it);
         cp_async_wait_all();
+        if (issues_tma) D3B_STAMP(3, it);
         fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(s));
       }
@@ -291,44 +326,54 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     }
   } else {
     // ===================== MMA issuer (one elected lane) =====================
-    // Every slot (offset, 64-channel slice) is accumulated from zero in its own TMEM buffer: the chain of
-    // truncating tensor-core accumulations is <= 12 MMAs long, everything beyond is summed by the accumulator warps.
-    constexpr uint32_t idesc = umma_idesc_f16(kOsTileM, COUT);
-    uint32_t it = 0;
+    // Every slot (offset, 64-channel slice) is accumulated from zero in its own TMEM buffer, its <= 12 MMAs spread over
+    // group's buffer (<= 24 chained truncating accumulations); everything beyond is summed by the accumulator warps.
+    constexpr uint32_t idesc2 = umma_idesc_f16(kOsTileM, 2 * COUT);   // A_hi x [B_hi | B_lo]
+    constexpr uint32_t idesc1 = umma_idesc_f16(kOsTileM, COUT);       // A_lo x B_hi
+    uint32_t it = 0, git = 0;          // slot counter (operand stages), group counter (accumulator buffers)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int n_slots = __popc(tile_mask[tile]) * n_kb;
-      for (int j = 0; j < n_slots; ++j, ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1u;
-        const uint32_t buf = it & 1u;
-        const int kb = j % n_kb;
-        const int n_ks = min(kOsKc / 16, (c_in - kb * kOsKc + 15) / 16);
-        D3B_WAIT(acc_empty(buf), ((it >> 1) & 1u) ^ 1u, 2);
-        D3B_WAIT(full_bar(s), ph, 3);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
-          const uint32_t a_lo = a_hi + kOsABytes;
-          const uint32_t b_hi = a_lo + kOsABytes;
-          const uint32_t b_lo = b_hi + COUT * 128;
-          const uint32_t d_addr = tmem_d + buf * Cfg::kAccCols;
-          for (int ks = 0; ks < n_ks; ++ks) {
-            const uint32_t adv = ks * 32;   // 16 f16 = 32 bytes along K inside the swizzle row
-            // small terms first, the dominant hi.hi product last
-            tc_mma_f16(d_addr, umma_desc_sw128(a_lo + adv), umma_desc_sw128(b_hi + adv), idesc, ks > 0 ? 1u : 0u);
-            tc_mma_f16(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_lo + adv), idesc, 1u);
-            tc_mma_f16(d_addr, umma_desc_sw128(a_hi + adv), umma_desc_sw128(b_hi + adv), idesc, 1u);
+      for (int j0 = 0; j0 < n_slots; j0 += Cfg::kFlush, ++git) {
+        const uint32_t buf = git & 1u;
+        if (lane == 0) D3B_STAMP(4, git);
+        D3B_WAIT(acc_empty(buf), ((git >> 1) & 1u) ^ 1u, 2);
+        if (lane == 0) D3B_STAMP(5, git);
+        const uint32_t d_addr = tmem_d + buf * Cfg::kBufCols;
+        const int j1 = min(j0 + Cfg::kFlush, n_slots);
+        for (int j = j0; j < j1; ++j, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          const int kb = j % n_kb;
+          const int n_ks = min(kOsKc / 16, (c_in - kb * kOsKc + 15) / 16);
+          D3B_WAIT(full_bar(s), ph, 3);
+          if (lane == 0) D3B_STAMP(6, it);
+          tc_fence_after();
+          {
+            // warp-uniform instruction stream (descriptor arithmetic stays in uniform registers); lane 0 issues
+            const uint32_t issue = lane == 0 ? 1u : 0u;
+            const uint32_t a_hi = smem_base + s * Cfg::kStageBytes;
+            const uint64_t da_hi = umma_desc_sw128(a_hi), da_lo = umma_desc_sw128(a_hi + kOsABytes);
+            const uint64_t db = umma_desc_sw128(a_hi + 2 * kOsABytes);
+#pragma unroll
+            for (int ks = 0; ks < kOsKc / 16; ++ks) {
+              if (ks < n_ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);   // 16 f16 = 32 bytes along K = 2 descriptor address units
+                tc_mma_f16_if(issue, d_addr, da_hi + adv, db + adv, idesc2, (j > j0 || ks > 0) ? 1u : 0u);
+                tc_mma_f16_if(issue, d_addr, da_lo + adv, db + adv, idesc1, 1u);
+              }
+            }
+            tc_commit_if(issue, empty_bar(s));      // frees the operand stage when these MMAs have read it
+            if (lane == 0) D3B_STAMP(7, it);
           }
-          tc_commit(empty_bar(s));      // frees the operand stage when these MMAs have read it
-          tc_commit(acc_full(buf));     // ... and hands the partial sums to the accumulator warps
         }
-        __syncwarp();
+        tc_commit_if(lane == 0 ? 1u : 0u, acc_full(buf));     // hands the group's partial sums to the accumulator warps
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  D3B_CTA_MARK(1);
   if (warp == Cfg::kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
@@ -338,7 +383,8 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
 // ---- first layer: fp32 rows with a handful of channels (C_in <= 16: the voxel mean, 4 or 5 features) -----------------
 // 2*27*C_in*C_out flops per row -- nothing for the tensor cores.  fp32 FFMA, output-stationary, same epilogue and
-// output format as the tcgen05 kernel.  Four lanes share a row (16 output channels each at C_out = 64).
+// output format as the tcgen05 kernel.  Four lanes share a (row, 16-column part), each taking every fourth offset (their
+// neighbour-index loads are independent and in flight together: the kernel is pure latency), combined by a fixed shuffle tree.
 template <int COUT>
 __global__ void __launch_bounds__(256)
 spconv_first16_kernel(const float* __restrict__ feat_in, const int* __restrict__ nbr, const int* __restrict__ n_out_p,
@@ -348,26 +394,44 @@ spconv_first16_kernel(const float* __restrict__ feat_in, const int* __restrict__
   extern __shared__ float w_s[];                 // [k_vol][c_in][COUT]
   for (int i = threadIdx.x; i < k_vol * c_in * COUT; i += blockDim.x) w_s[i] = weight[i];
   __syncthreads();
-  constexpr int kParts = COUT / 16;              // threads per row
+  constexpr int kParts = COUT / 16;              // 16-column parts of a row
+  constexpr int kSub = 4;                        // lanes per (row, part): lane `sub` takes the offsets k = sub, sub + 4, ...
+  constexpr int kMaxK = 8;                       // ceil(32 / 4) offsets per lane at most
   const int n_out = min(*n_out_p, out_cap);
-  const long long total = (long long)n_out * kParts;
+  const long long items = (long long)n_out * kParts;
+  const long long items_pad = (items + 7) / 8 * 8;          // whole warps (8 items each) run the shuffles together
   bool ovf = false;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(e / kParts), col = (int)(e % kParts) * 16;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < items_pad * kSub; e += (long long)gridDim.x * blockDim.x) {
+    const long long item = e / kSub;
+    const int sub = (int)(e % kSub);
+    const bool on = item < items;
+    const int o = on ? (int)(item / kParts) : 0, col = (int)(item % kParts) * 16;
+    int src[kMaxK];
+#pragma unroll
+    for (int t = 0; t < kMaxK; ++t) {            // the neighbour indices first: independent loads, all in flight together
+      const int k = sub + t * kSub;
+      src[t] = (on && k < k_vol) ? __ldg(nbr + (size_t)k * out_cap + o) : -1;
+    }
     float acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-    for (int k = 0; k < k_vol; ++k) {
-      const int src = __ldg(nbr + (size_t)k * out_cap + o);
-      if (src < 0) continue;
+#pragma unroll
+    for (int t = 0; t < kMaxK; ++t) {
+      if (src[t] < 0) continue;
+      const int k = sub + t * kSub;
       for (int ci = 0; ci < c_in; ++ci) {
-        const float a = __ldg(feat_in + (size_t)src * c_in + ci);
+        const float a = __ldg(feat_in + (size_t)src[t] * c_in + ci);
         const float* w = w_s + ((size_t)k * c_in + ci) * COUT + col;
 #pragma unroll
         for (int q = 0; q < 16; ++q) acc[q] = fmaf(a, w[q], acc[q]);
       }
     }
-    ovf |= epilogue16(acc, epi, (size_t)o * COUT, col, out_hi, out_lo, out_f32);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {               // fixed-order tree over the four offset classes
+      acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 1);
+      acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 2);
+    }
+    if (on && sub == 0) ovf |= epilogue16(acc, epi, (size_t)o * COUT, col, out_hi, out_lo, out_f32);
   }
   if (ovf && overflow) atomicOr(overflow, 1);
 }
@@ -481,7 +545,7 @@ static int launch_first16(const d3b_conv16_params* p, const int32_t* nbr, const 
   static SmemOptIn optin;
   D3B_REQUIRE(smem <= 160 * 1024, "first-layer sparse conv: weights (%zu bytes) do not fit in shared memory", smem);
   D3B_CUDA(ensure_dynamic_smem(spconv_first16_kernel<COUT>, smem, optin));
-  const int grid = grid_for((long long)out_cap * (COUT / 16), 256, 4);
+  const int grid = grid_for((long long)out_cap * (COUT / 16) * 4, 256, 8);
   spconv_first16_kernel<COUT><<<grid, 256, smem, stream>>>(p->in_f32, nbr, n_out, out_cap, p->c_in, p->k_vol, p->weight,
                                                          epi_of(p), (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32,
                                                          p->overflow);
@@ -589,6 +653,17 @@ extern "C" int d3b_debug_fault_spconv16(unsigned int* host8) {
   cudaError_t e = cudaMemcpyFromSymbol(host8, d3b::g_d3b_fault, 32);
   unsigned int zeros[8] = {0};
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(d3b::g_d3b_fault, zeros, 32);
+  return (int)e;
+}
+extern "C" int d3b_debug_cta_ns_spconv16(unsigned long long* host512) {
+  return (int)cudaMemcpyFromSymbol(host512, d3b::g_d3b_cta_ns, sizeof(unsigned long long) * 512);
+}
+extern "C" int d3b_debug_trace_spconv16(long long* host, int clear) {
+  cudaError_t e = cudaMemcpyFromSymbol(host, d3b::g_d3b_trace, sizeof(long long) * 16 * 512);
+  if (e == cudaSuccess && clear) {
+    static long long zeros[16 * 512];
+    e = cudaMemcpyToSymbol(d3b::g_d3b_trace, zeros, sizeof(zeros));
+  }
   return (int)e;
 }
 #endif

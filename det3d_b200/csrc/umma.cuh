@@ -53,8 +53,26 @@ __device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, uns
   }
 }
 #define D3B_WAIT(bar, parity, code) mbar_wait_dbg(bar, parity, code)
+// clock-stamp trace of CTA 0 (development library only): g_d3b_trace[event][slot] = clock64()
+static __device__ long long g_d3b_trace[16 * 512];
+// per-CTA wall-clock span (ns, globaltimer): [2 * cta] = entry, [2 * cta + 1] = exit
+static __device__ unsigned long long g_d3b_cta_ns[2 * 256];
+__device__ __forceinline__ void d3b_cta_mark(int which) {
+  if (threadIdx.x == 0 && blockIdx.x < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_d3b_cta_ns[2 * blockIdx.x + which] = t;
+  }
+}
+#define D3B_CTA_MARK(which) d3b_cta_mark(which)
+#define D3B_STAMP(ev, slot)                                                                        \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (unsigned)(slot) < 512u) g_d3b_trace[(ev) * 512 + (slot)] = clock64();  \
+  } while (0)
 #else
 #define D3B_WAIT(bar, parity, code) mbar_wait(bar, parity)
+#define D3B_STAMP(ev, slot)
+#define D3B_CTA_MARK(which)
 #endif
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -120,6 +138,30 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for a warp-uniform issue loop: every lane runs the same instruction stream (descriptor arithmetic
+// stays uniform), only the lane with issue != 0 executes the tcgen05 instruction.
+__device__ __forceinline__ void tc_mma_f16_if(uint32_t issue, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t issue, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue)
+      : "memory");
+}
+// Expected relative loss of one truncating tensor-core accumulation: measured on both kernels against float64
+// (scratch/conv16_accuracy.py) the mean signed error is -1.5e-8 = -2^-26 per MMA chained into an accumulator, for chains of
+// 3 .. 648 -- the adder keeps two guard bits and truncates.  The accumulator warps add it back when they drain a buffer.
+constexpr float kTruncLossPerMma = 1.4901161e-8f;   // 2^-26
+
 // tcgen05.ld without the wait: issue several, then tc_ld_wait() once
 __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(

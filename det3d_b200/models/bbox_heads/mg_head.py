@@ -45,6 +45,29 @@ class Head(nn.Module):
         return out
 
 
+class _PackedDetections(dict):
+    """dict(packed, boxes, scores, labels, valid) over the packed device tensor; `labels` (int64) and `valid` (bool) are
+    materialised on first access only -- the serving path ships `packed` as is and would pay two extra launches per step."""
+
+    def __init__(self, packed, nd):
+        super().__init__(packed=packed, boxes=packed[..., :nd], scores=packed[..., nd])
+        self._nd = nd
+
+    def __missing__(self, key):
+        packed, nd = dict.__getitem__(self, "packed"), self._nd
+        if key == "labels":
+            value = packed[..., nd + 1].long()
+        elif key == "valid":
+            value = packed[..., nd + 2] > 0.5
+        else:
+            raise KeyError(key)
+        self[key] = value
+        return value
+
+    def __contains__(self, key):
+        return key in ("labels", "valid") or dict.__contains__(self, key)
+
+
 @HEADS.register_module
 class MultiGroupHead(nn.Module):
     def __init__(self, mode="3d", in_channels=[128], norm_cfg=None, tasks=[], weights=[], num_classes=[1],
@@ -277,8 +300,7 @@ class MultiGroupHead(nn.Module):
             _lib.check(st, "d3b_predict_task")
             row_offset += post
             flag += n_cls
-        return dict(packed=packed, boxes=packed[..., :nd], scores=packed[..., nd], labels=packed[..., nd + 1].long(),
-                    valid=packed[..., nd + 2] > 0.5)
+        return _PackedDetections(packed, nd)
 
     def _predict_device_torch(self, example, preds_dicts, test_cfg):
         outs = []
