@@ -461,6 +461,9 @@ def main():
             evs.append((a, b))
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        if os.environ.get("D3B_BENCH_DEBUG"):
+            print(f"[bench] rank {rank} {'e2e' if e2e else 'device'} per-step ms: "
+                  + " ".join(f"{a.elapsed_time(b):.3f}" for a, b in evs), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -120,6 +120,7 @@ SIGNATURES = {
     "d3b_last_error": (C.c_char_p, []),
     "d3b_abi_version": (C.c_int, []),
     "d3b_launch_count": (C.c_ulonglong, []),
+    "d3b_set_pdl": (None, [C.c_int]),
     "d3b_voxelize_workspace_bytes": (_sz, [C.POINTER(VoxelCfg), _i32, _i32]),
     "d3b_voxelize": (C.c_int, [C.POINTER(VoxelCfg), _vp, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3b_ingest_workspace_bytes": (_sz, [_i32]),

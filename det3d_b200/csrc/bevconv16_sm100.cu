@@ -108,6 +108,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * kBvAStages + 2 * Cfg::kBStages + 8));
 
   D3B_CTA_MARK(0);
+  pdl_launch_dependents();           // the next kernel of the stream may start its prologue behind this one's tail
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_group = g.batch * g.tiles_y * g.tiles_x;
   const int n_tiles = tiles_per_group * g.groups;
@@ -134,6 +135,7 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_wait_prior_grid();             // everything below reads the previous layer's planes or writes buffers it may still read
 
   // tile -> (group, sample, y0, x0)
   auto decode = [&](int tile, int& grp, int& b, int& y0, int& x0) {
@@ -408,8 +410,9 @@ static int launch_bev(const d3b_bev16_params* p, const BvGeom& g, cudaStream_t s
   e.bias = p->bias; e.scale = p->scale; e.shift = p->shift; e.acc_scale = p->acc_scale; e.relu = p->relu;
   const int n_tiles = g.batch * g.tiles_y * g.tiles_x * g.groups;
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  bev_conv16_kernel<KS, STRIDE, COUT><<<grid, kBvThreads, Cfg::kSmemBytes, stream>>>(
-      tm_hi, tm_lo, g, (const __half*)p->weight_packed, e, (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, p->overflow);
+  D3B_CUDA(launch_maybe_pdl(bev_conv16_kernel<KS, STRIDE, COUT>, dim3(grid), dim3(kBvThreads), Cfg::kSmemBytes, stream, tm_hi,
+                            tm_lo, g, (const __half*)p->weight_packed, e, (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32,
+                            (int*)p->overflow));
   D3B_LAUNCH_CHECK();
   return D3B_OK;
 }

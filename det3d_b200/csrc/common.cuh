@@ -63,6 +63,32 @@ static inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, SmemO
   return e;
 }
 
+// ---- programmatic dependent launch --------------------------------------------------------------------------------
+// The convolution kernels run back to back on one stream.  Launched with programmatic stream serialisation, kernel N+1 is
+// scheduled as soon as every CTA of kernel N has executed `griddepcontrol.launch_dependents` (they do so on entry): its
+// launch latency and its prologue (barrier init, TMEM allocation, rulebook staging -- nothing that reads kernel N's
+// output) overlap kernel N's tail; `griddepcontrol.wait` (executed by every thread before it touches activations) then
+// blocks until kernel N has completed and its writes are visible.  Inside a captured CUDA graph the edge becomes a
+// programmatic dependency.  d3b_set_pdl(0) turns it off (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- device constants --------------------------------------------------------
 constexpr int kNumSMs = 148;  // B200
 

@@ -17,12 +17,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 }  // namespace d3b
 
 extern "C" const char* d3b_last_error(void) { return d3b::g_error; }
 extern "C" int d3b_abi_version(void) { return 2; }
+extern "C" void d3b_set_pdl(int on) { d3b::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 extern "C" unsigned long long d3b_launch_count(void) {
   return d3b::g_launches.load(std::memory_order_relaxed);
 }

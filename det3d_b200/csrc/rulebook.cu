@@ -201,67 +201,56 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* smem /*[32]*/, i
   return off + incl - v;
 }
 
+// Exclusive popcount scan of the bitmap in ONE launch (decoupled look-back): a block counts its 4096 words, publishes the
+// total, sums its
+// predecessors' totals as they appear (they were dispatched earlier, so they are running or done), writes the word
+// prefixes; the last block writes the row count.  block_sums must hold -1 ("not published") on entry (0xff memset).
 __global__ void __launch_bounds__(kScanThreads)
-rb_scan_block_sums(const unsigned int* __restrict__ bitmap, long long n_words,
-                   int* __restrict__ block_sums) {
+rb_scan_fused(const unsigned int* __restrict__ bitmap, long long n_words, int* block_sums, int out_cap,
+              int* __restrict__ n_out, int* __restrict__ word_prefix) {
   __shared__ int smem[32];
-  const long long base = (long long)blockIdx.x * kScanWordsPerBlock + threadIdx.x * kScanWordsPerThread;
-  int cnt = 0;
-  if (base + 3 < n_words) {
-    const uint4 v = *reinterpret_cast<const uint4*>(bitmap + base);
-    cnt = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-  } else {
-    for (int j = 0; j < kScanWordsPerThread; ++j)
-      if (base + j < n_words) cnt += __popc(bitmap[base + j]);
-  }
-  int total;
-  block_exclusive_scan(cnt, smem, total);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-// single CTA: exclusive scan of block sums in place; writes n_out[0]=min(total,cap), [1]=total
-__global__ void __launch_bounds__(kScanThreads)
-rb_scan_sums(int* block_sums, int n_blocks, int out_cap, int* n_out) {
-  __shared__ int smem[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n_blocks; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int v = i < n_blocks ? block_sums[i] : 0;
-    int total;
-    const int ex = block_exclusive_scan(v, smem, total);
-    if (i < n_blocks) block_sums[i] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    n_out[0] = carry < out_cap ? carry : out_cap;
-    n_out[1] = carry;
-  }
-}
-
-// prefix pass: word_prefix[w] = number of set bits before word w (block offsets already scanned)
-__global__ void __launch_bounds__(kScanThreads)
-rb_scan_prefix(const unsigned int* __restrict__ bitmap, long long n_words,
-               const int* __restrict__ block_offsets, int* __restrict__ word_prefix) {
-  __shared__ int smem[32];
+  __shared__ int s_offset;
   const long long base = (long long)blockIdx.x * kScanWordsPerBlock + threadIdx.x * kScanWordsPerThread;
   unsigned int w[kScanWordsPerThread];
   int cnt = 0;
+  if (base + 3 < n_words) {
+    const uint4 v = *reinterpret_cast<const uint4*>(bitmap + base);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else {
 #pragma unroll
-  for (int j = 0; j < kScanWordsPerThread; ++j) {
-    w[j] = base + j < n_words ? bitmap[base + j] : 0u;
-    cnt += __popc(w[j]);
+    for (int j = 0; j < kScanWordsPerThread; ++j) w[j] = base + j < n_words ? bitmap[base + j] : 0u;
   }
+#pragma unroll
+  for (int j = 0; j < kScanWordsPerThread; ++j) cnt += __popc(w[j]);
   int total;
-  int rank = block_offsets[blockIdx.x] + block_exclusive_scan(cnt, smem, total);
+  const int ex = block_exclusive_scan(cnt, smem, total);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicExch(&block_sums[blockIdx.x], total);          // publish
+  }
+  if (threadIdx.x < 32) {
+    int sum = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += 32) {
+      int v;
+      do { v = *reinterpret_cast<volatile int*>(&block_sums[j]); } while (v < 0);
+      sum += v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (threadIdx.x == 0) s_offset = sum;
+  }
+  __syncthreads();
+  int rank = s_offset + ex;
 #pragma unroll
   for (int j = 0; j < kScanWordsPerThread; ++j) {
     if (base + j >= n_words) break;
     word_prefix[base + j] = rank;
     rank += __popc(w[j]);
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    const int all = s_offset + total;
+    n_out[0] = all < out_cap ? all : out_cap;
+    n_out[1] = all;
   }
 }
 
@@ -457,12 +446,9 @@ extern "C" int d3b_rulebook_conv(const int32_t* in_coors, const int32_t* n_in, i
   rb_mark_outputs<<<grid_for((long long)in_cap * g.kvol, 256), 256, 0, stream>>>(
       in_coors, n_in, in_cap, out, g, out_index->bitmap);
   D3B_LAUNCH_CHECK();
-  rb_scan_block_sums<<<n_blocks, kScanThreads, 0, stream>>>(out_index->bitmap, n_words, block_sums);
-  D3B_LAUNCH_CHECK();
-  rb_scan_sums<<<1, kScanThreads, 0, stream>>>(block_sums, n_blocks, out_cap, n_out);
-  D3B_LAUNCH_CHECK();
-  rb_scan_prefix<<<n_blocks, kScanThreads, 0, stream>>>(out_index->bitmap, n_words, block_sums,
-                                                        out_index->word_prefix);
+  D3B_CUDA(cudaMemsetAsync(block_sums, 0xff, (size_t)n_blocks * 4, stream));       // -1 = "not published yet"
+  rb_scan_fused<<<n_blocks, kScanThreads, 0, stream>>>(out_index->bitmap, n_words, block_sums, out_cap, n_out,
+                                                       out_index->word_prefix);
   D3B_LAUNCH_CHECK();
   rb_emit_coors<<<grid_for(n_words, 256), 256, 0, stream>>>(out_index->bitmap, out_index->word_prefix, n_words, out,
                                                            out_cap, out_coors);

@@ -168,11 +168,13 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto acc_full = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
   auto acc_empty = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+  const uint32_t nbr_bar = bar_base + 8u * (2 * Cfg::kStages + 4);                 // neighbour rows of the tile have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 5));
   int* koff_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 128);   // [32] active offsets
   int* nbr_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);    // [32][128] neighbour rows
 
   D3B_CTA_MARK(0);
+  pdl_launch_dependents();           // the next kernel of the stream may start its prologue behind this one's tail
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = min(*n_out_p, out_cap);
   const int n_tiles = (n_out + kOsTileM - 1) / kOsTileM;
@@ -186,6 +188,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       mbar_init(acc_full(b), 1);                       // tcgen05.commit of a slot's MMAs
       mbar_init(acc_empty(b), 32 * Cfg::kEpiWarps);    // every accumulator warp has read the slot's partial sums
     }
+    mbar_init(nbr_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == Cfg::kMmaWarp) {
@@ -201,6 +204,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
   if (warp < Cfg::kEpiWarps) {
     // ===================== accumulator warps =====================
+    pdl_wait_prior_grid();           // (residual planes / output buffers belong to earlier kernels)
     // Per slot: TMEM partial sums -> fp32 registers (round-to-nearest adds).  At the end of the tile: fused
     // bias / BN / residual / ReLU, split into f16 planes, one store per output row.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
@@ -260,6 +264,8 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     const int ptid = threadIdx.x - 32 * Cfg::kGatherWarp0;      // 0 .. 64 * kGroups - 1
     const int c_in_pad = (c_in + 15) & ~15;
     uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
+    uint32_t tile_count = 0;                       // tiles with work so far (phase of nbr_bar)
+    const bool bulk_nbr = (out_cap & 3) == 0;      // 16-byte aligned rows: cp.async.bulk can fetch them
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * kOsTileM;
       const unsigned int mask = tile_mask[tile];
@@ -271,15 +277,28 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
       if (ptid < 32) {                                    // n-th active offset of the tile
         unsigned int m = mask;
         for (int t = ptid; t > 0; --t) m &= m - 1;
-        if (ptid < n_off) koff_s[ptid] = __ffs(m) - 1;
+        const int k = __ffs(m) - 1;
+        if (ptid < n_off) koff_s[ptid] = k;
+        // neighbour rows of the tile by bulk copy (one 512-byte copy per active offset, no thread touches them)
+        const int rows = min(kOsTileM, out_cap - row0);
+        if (bulk_nbr && n_off > 0 && ptid == 0) mbar_arrive_expect_tx(nbr_bar, (uint32_t)(n_off * rows * 4));
+        __syncwarp();
+        if (bulk_nbr && ptid < n_off)
+          tma_bulk_g2s(smem_u32(nbr_s + ptid * kOsTileM), nbr + (size_t)k * out_cap + row0, (uint32_t)(rows * 4), nbr_bar);
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
+      if (bulk_nbr) {
+        if (n_off > 0) D3B_WAIT(nbr_bar, tile_count & 1u, 5);
+      } else {
+        asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
 #pragma unroll 8
-      for (int idx = ptid; idx < n_off * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {   // independent loads
-        const int r = idx & 127;
-        nbr_s[idx] = (row0 + r < n_out) ? __ldg(nbr + (size_t)koff_s[idx >> 7] * out_cap + row0 + r) : -1;
+        for (int idx = ptid; idx < n_off * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {   // independent loads
+          const int r = idx & 127;
+          nbr_s[idx] = __ldg(nbr + (size_t)koff_s[idx >> 7] * out_cap + min(row0 + r, out_cap - 1));
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
+      if (n_off > 0) ++tile_count;
+      if (tile == (int)blockIdx.x) pdl_wait_prior_grid();     // rulebook rows staged; the activations need the previous layer done
 
       for (int j = (int)((group + Cfg::kGroups - (it0 % Cfg::kGroups)) % Cfg::kGroups); j < n_slots; j += Cfg::kGroups) {
         const int n = j / n_kb, kb = j - n * n_kb;
@@ -308,7 +327,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int row = row_base + q4 * 4 + u;
-              const bool live = srcs[u] >= 0 && col_live;
+              const bool live = srcs[u] >= 0 && col_live && row0 + row < n_out;    // (rows past n_out hold stale indices)
               const size_t off = live ? (size_t)srcs[u] * c_in + ch : 0;
               const uint32_t dst = stage + sw128_offset(row, c);
               cp_async16(dst, in_hi + off, live ? 16u : 0u);
@@ -531,9 +550,10 @@ static int launch_os16(const d3b_conv16_params* p, const int32_t* nbr, const uin
   const int n_tiles = div_up(out_cap, kOsTileM);
   const int grid = n_tiles < kNumSMs ? (n_tiles > 0 ? n_tiles : 1) : kNumSMs;
   const int n_kb = (p->c_in + kOsKc - 1) / kOsKc;
-  spconv_os16_kernel<COUT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      (const __half*)p->in_hi, (const __half*)p->in_lo, nbr, tile_mask, n_out, out_cap, p->c_in, n_kb,
-      (const __half*)p->weight_packed, epi_of(p), (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, p->overflow);
+  D3B_CUDA(launch_maybe_pdl(spconv_os16_kernel<COUT>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream,
+                            (const __half*)p->in_hi, (const __half*)p->in_lo, (const int*)nbr, (const unsigned int*)tile_mask,
+                            (const int*)n_out, (int)out_cap, (int)p->c_in, n_kb, (const __half*)p->weight_packed, epi_of(p),
+                            (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, (int*)p->overflow));
   D3B_LAUNCH_CHECK();
   return D3B_OK;
 }

@@ -36,6 +36,9 @@ int d3b_abi_version(void);
 /* Number of kernels this library has launched since load (process-wide);
  * bench.py reports the delta over the timed region as "gpu_launches". */
 unsigned long long d3b_launch_count(void);
+/* Programmatic dependent launch between consecutive convolution kernels of a stream (default on): the next kernel's
+ * launch latency and prologue overlap the previous kernel's tail; results are unaffected. 0 = plain stream order. */
+void d3b_set_pdl(int on);
 
 /* ========================================================================= *
  * 1. Voxelizer
