@@ -406,9 +406,9 @@ def main():
         """The job's one exchange step: all ranks' detections of the last `n_rows` steps, gathered over NCCL."""
         g = all_gather_detections(state["ring"][:n_rows].reshape(n_rows * B, *state["ring"].shape[2:]))
         if e2e:
-            if state["gathered_pinned"] is None or state["gathered_pinned"].shape != g.shape:
-                state["gathered_pinned"] = torch.empty(g.shape, dtype=torch.float32, pin_memory=True)
-            state["gathered_pinned"].copy_(g, non_blocking=True)
+            if state["gathered_pinned"] is None or state["gathered_pinned"].numel() < g.numel():
+                state["gathered_pinned"] = torch.empty(g.numel(), dtype=torch.float32, pin_memory=True)
+            state["gathered_pinned"][:g.numel()].view(g.shape).copy_(g, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return g
 
@@ -474,10 +474,14 @@ def main():
     if rank == 0:
         sampler.start()
     warm = max(args.warmup, 3)
+    ring_steps = max(warm, args.steps)
     for s in range(warm):
-        step_device(s, warm)
-        step_e2e(s, warm)
-    exchange(warm, True)
+        step_device(s, ring_steps)
+        step_e2e(s, ring_steps)
+    ge0 = max(0, args.gather_every)
+    exchange(args.steps if ge0 <= 0 else min(ge0, args.steps), True)   # same shapes as the timed exchange: the device ring,
+    #                                                                  the NCCL buffers and the pinned landing buffer exist
+    #                                                                  before the clock starts (cudaHostAlloc alone is ~90 ms)
     if state["overflowed"]:
         raise SystemExit("bench.py: the FP16x3 kernels flagged an f16-range overflow on the synthetic workload; run with --math tf32x3")
 
