@@ -221,16 +221,27 @@ topk_finish_kernel(const unsigned long long* __restrict__ part, const int* __res
   // order: one broadcast shared-memory read per comparison, no barriers, and the candidates spread over the sample's
   // CTAs (a bitonic network over 8192 entries in one CTA cost 59 us here; 2048 entries 21 us).
   __syncthreads();
-  for (int c = cta * kTopkThreads + tid; c < m; c += n_cta * kTopkThreads) {
-    const unsigned long long x = buf[c];
+  // T threads (consecutive lanes) share a candidate, each counting over 1/T of the list: the sample's threads are all busy
+  // whatever the list length (k + the rest of the pivot bin: 1.1k .. 8k entries)
+  const int total = n_cta * kTopkThreads;
+  int T = 1;
+  while (T < 32 && m * (T * 2) <= total) T <<= 1;
+  const int gid = cta * kTopkThreads + tid;
+  const int sub = gid & (T - 1);
+  const int chunk = ((m + T - 1) / T + 1) & ~1;                 // even, so the 16-byte reads stay aligned
+  const int j_lo = min(sub * chunk, m), j_hi = min(j_lo + chunk, m);
+  for (int base = 0; base < m; base += total / T) {            // warp-uniform trip count
+    const int c = base + gid / T;
+    const unsigned long long x = c < m ? buf[c] : ~0ull;
     int rank = 0;
-    int j = 0;
-    for (; j + 2 <= m; j += 2) {
+    int j = j_lo;
+    for (; j + 2 <= j_hi; j += 2) {
       const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(buf + j);
       rank += (y.x > x ? 1 : 0) + (y.y > x ? 1 : 0);
     }
-    if (j < m) rank += buf[j] > x ? 1 : 0;
-    if (rank < k) emit(rank, x);
+    if (j < j_hi) rank += buf[j] > x ? 1 : 0;
+    for (int d = 1; d < T; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+    if (sub == 0 && c < m && rank < k) emit(rank, x);
   }
   for (int j = m + cta * kTopkThreads + tid; j < k; j += n_cta * kTopkThreads) emit(j, 0ull);   // fewer candidates than k
 }

@@ -9,11 +9,11 @@
 // products with fp32 atomics: summation order -- hence the last bits -- changed run to run, its 14 launches needed 8
 // buffer-clearing launches and a deferred epilogue, and at lidar densities (~100-160 work items per layer) it was bound
 // by the RED issue rate and two dependent L2 round trips per item.  Here one CTA owns 128 output rows and walks the
-// kernel offsets present in the tile (tile_mask); every offset is one pipeline slot: four groups of gather warps copy
+// kernel offsets present in the tile (tile_mask); an (offset, 64-channel slice) is one pipeline slot: gather warps copy
 // the 128 input rows (or zeros where the offset has no neighbour) with 16-byte cp.async straight into a K-major,
-// 128B-swizzled tile, one thread issues the MMAs, accumulation stays in TMEM across all offsets, and the fused
-// bias/BN/residual/ReLU epilogue writes each output row once.  No atomics, fixed summation order: bit-identical
-// results run to run.
+// 128B-swizzled tile, one warp issues the MMAs, dedicated accumulator warps keep the running sums in registers, and the
+// fused bias/BN/residual/ReLU epilogue writes each output row once.  No atomics, fixed summation order: bit-identical
+// results run to run, and a row's bits depend on its own neighbourhood only (not on the rows sharing its tile).
 //
 // fp32-equivalent accuracy on the f16 pipe (twice the tf32 rate, half the operand bytes).  Activations live in HBM as
 // two f16 planes, hi = f16(x) and lo = f16(x - hi) (22 significant bits, written once by the producing layer's
@@ -24,15 +24,18 @@
 //
 // Accumulation.  The tensor core adds every MMA's partial sum into the fp32 TMEM accumulator with truncation (round
 // toward zero): measured on this path, the relative error of a layer grew linearly with the number of MMAs chained into
-// one accumulator (27 offsets x 8..24 MMAs -> 2e-5 .. 7e-5 over the encoder), a systematic shrink that 20 layers turn
-// into > 1e-4.  So the chain is cut at ONE pipeline slot (<= 12 MMAs): each slot accumulates from zero in its own TMEM
-// buffer (two buffers, so slot j+1 runs while slot j is drained) and dedicated accumulator warps add the slots'
-// partial sums into fp32 registers with round-to-nearest -- the same summation structure as the reference's
-// per-offset GEMM + scatter-add, with a fixed order.
+// one accumulator, about -2^-26 per MMA (27 offsets x 8..24 MMAs -> 2e-5 .. 7e-5 over the encoder), a systematic shrink
+// that 20 layers turn into > 1e-4.  So (a) the chain is bounded: a TMEM buffer collects kFlush = 3 slots of the FULL slot
+// enumeration (fixed ranges, whichever of them the tile mask activates), then the accumulator warps add it into fp32
+// registers with round-to-nearest while the next group fills the other buffer -- the summation structure of the
+// reference's per-offset GEMM + scatter-add, in a fixed order; and (b) the mean of the truncation is undone: a row's
+// partial sum is scaled by 1 + n * 2^-26, n = the MMAs that contributed to THAT row (absent neighbours add exact zeros).
 //
-// Roles: 4 or 8 accumulator warps (TMEM -> registers every slot, fused epilogue at the end of the tile), one gather
-// group of 2 warps per pipeline stage (slot j -> group j % stages; 4 stages, 3 at C_out = 128; pure cp.async issue, so few
-// threads suffice and the register file goes to the accumulators), 1 MMA warp (also owns TMEM); persistent grid <= 148 CTAs.
+// Roles: 4 or 8 accumulator warps (first, so they get the registers), one gather group of 2 warps per pipeline stage
+// (slot j -> group j % stages; 4 stages, 3 at C_out = 128; pure cp.async issue), 1 MMA warp (also owns TMEM); persistent
+// grid <= 148 CTAs.  Per k-step two MMAs: A_hi x [B_hi | B_lo] (N = 2 C_out) and A_lo x B_hi (N = C_out).  C_in = 16 / 32
+// layers pack 4 / 2 kernel offsets into one slot (os16_pack).  The tile's rulebook rows arrive by cp.async.bulk; the
+// kernel is launched with programmatic stream serialisation (prologue overlaps the previous layer's tail).
 // Algorithmic bytes per layer: N_in*C_in*4 + N_out*C_out*4 + P*8 + K*C_in*C_out*4.
 #include "umma.cuh"
 
@@ -153,11 +156,27 @@ __device__ __forceinline__ bool epilogue16(float (&v)[16], const OsEpi& e, size_
   return ovf;
 }
 
+// Offset packing.  A pipeline slot always moves 128 rows x 128 bytes per plane and costs about the same whatever part
+// of it is live, so layers with C_in = 16 / 32 put `pack` = 4 / 2 kernel offsets side by side along K: slot p holds the
+// rows of offsets p*pack .. p*pack + pack - 1 (16-byte chunks [sub * 8/pack, (sub+1) * 8/pack) of every row come from
+// offset p*pack + sub), the weight slice is the matching K-concatenation (zero for offsets >= k_vol), and a 3x3x3 layer
+// runs 14 / 7 slots per tile instead of 27.  A slot is skipped when none of its offsets occurs in the tile.
+__host__ __device__ inline int os16_pack(int c_in, int k_vol) {
+  return k_vol > 1 && (c_in == 16 || c_in == 32) ? kOsKc / c_in : 1;
+}
+__device__ __forceinline__ unsigned int os16_slot_mask(unsigned int offset_mask, int pack) {
+  if (pack == 1) return offset_mask;
+  unsigned int r = 0u;
+  const unsigned int grp = (1u << pack) - 1u;
+  for (int p = 0; p * pack < 32; ++p) r |= ((offset_mask >> (p * pack)) & grp) ? (1u << p) : 0u;
+  return r;
+}
+
 template <int COUT>
 __global__ void __launch_bounds__(OsCfg<COUT>::kThreads, 1)
 spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, const int* __restrict__ nbr,
                    const unsigned int* __restrict__ tile_mask, const int* __restrict__ n_out_p, int out_cap, int c_in,
-                   int n_kb, const __half* __restrict__ packed, OsEpi epi, __half* __restrict__ out_hi,
+                   int n_kb, int pack, int k_vol, const __half* __restrict__ packed, OsEpi epi, __half* __restrict__ out_hi,
                    __half* __restrict__ out_lo, float* __restrict__ out_f32, int* __restrict__ overflow) {
   using Cfg = OsCfg<COUT>;
   extern __shared__ uint8_t smem_raw[];
@@ -178,6 +197,8 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = min(*n_out_p, out_cap);
   const int n_tiles = (n_out + kOsTileM - 1) / kOsTileM;
+  const int c_eff = c_in * pack;                 // K extent of the slots (64 when offsets are packed)
+  const int n_full = ((k_vol + pack - 1) / pack) * n_kb;     // slots of a tile in which every offset occurs
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -212,24 +233,39 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     bool ovf = false;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n_slots = __popc(tile_mask[tile]) * n_kb;
+      const unsigned int smask = os16_slot_mask(tile_mask[tile], pack);
       const int o = tile * kOsTileM + quad * 32 + lane;
       float acc[Cfg::kCols];
 #pragma unroll
       for (int q = 0; q < Cfg::kCols; ++q) acc[q] = 0.f;
-      const int n_groups = (n_slots + Cfg::kFlush - 1) / Cfg::kFlush;
-      for (int gi = 0; gi < n_groups; ++gi, ++it) {
+      // which kernel offsets reach THIS row: an absent neighbour contributes exact zeros (nothing is truncated), so the
+      // truncation correction of a group counts the row's own live k-steps -- with the fixed grouping below, a row's bits
+      // depend on its own neighbourhood only, never on which other rows share its tile (batch composition)
+      unsigned int live = 0u;
+      if (o < n_out) {
+#pragma unroll 9
+        for (int k = 0; k < k_vol; ++k) live |= (__ldg(nbr + (size_t)k * out_cap + o) >= 0 ? 1u : 0u) << k;
+      }
+      for (int f0 = 0; f0 < n_full; f0 += Cfg::kFlush) {
+        int n_active = 0, n_ks_row = 0;                 // slots of the group present in the tile; this row's live k-steps
+        for (int f = f0; f < min(f0 + Cfg::kFlush, n_full); ++f) {
+          const int sp = n_kb == 1 ? f : f / n_kb, kb = f - sp * n_kb;      // (no division on the usual path)
+          if (!((smask >> sp) & 1u)) continue;
+          ++n_active;
+          if (pack == 1)
+            n_ks_row += ((live >> sp) & 1u) ? min(kOsKc / 16, (c_eff - kb * kOsKc + 15) / 16) : 0;
+          else
+            n_ks_row += __popc((live >> (sp * pack)) & ((1u << pack) - 1u)) * (kOsKc / 16 / pack);
+        }
+        if (n_active == 0) continue;
         const uint32_t buf = it & 1u;
         if (warp == 0 && lane == 0) D3B_STAMP(8, it);
         D3B_WAIT(acc_full(buf), (it >> 1) & 1u, 4);
         if (warp == 0 && lane == 0) D3B_STAMP(9, it);
         tc_fence_after();
         const uint32_t t0 = tmem_d + buf * Cfg::kBufCols + ((uint32_t)(quad * 32) << 16) + col0;
-        int n_ks_sum = 0;                               // k-steps chained into this buffer
-        for (int j = gi * Cfg::kFlush; j < min((gi + 1) * Cfg::kFlush, n_slots); ++j)
-          n_ks_sum += min(kOsKc / 16, (c_in - (j % n_kb) * kOsKc + 15) / 16);
-        const float f_hh = 1.f + 2.f * (float)n_ks_sum * kTruncLossPerMma;     // two MMAs per k-step land on these columns
-        const float f_hl = 1.f + (float)n_ks_sum * kTruncLossPerMma;
+        const float f_hh = 1.f + 2.f * (float)n_ks_row * kTruncLossPerMma;     // two MMAs per k-step land on these columns
+        const float f_hl = 1.f + (float)n_ks_row * kTruncLossPerMma;
 #pragma unroll
         for (int c0 = 0; c0 < Cfg::kCols; c0 += 16) {
           uint32_t r0[16], r1[16];
@@ -243,6 +279,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         tc_fence_before();
         mbar_arrive(acc_empty(buf));               // the MMA thread may overwrite this buffer
         if (warp == 0 && lane == 0) D3B_STAMP(10, it);
+        ++it;
       }
       if (o < n_out) {
 #pragma unroll
@@ -263,13 +300,16 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     const bool issues_tma = (wq == 0 && lane == 0);
     const int ptid = threadIdx.x - 32 * Cfg::kGatherWarp0;      // 0 .. 64 * kGroups - 1
     const int c_in_pad = (c_in + 15) & ~15;
+    const int cpo = 8 / pack;                                   // 16-byte chunks per packed offset
+    const int sub = c / cpo;                                    // which of the slot's offsets feeds this thread's chunk
+    const int c_src = c - sub * cpo;                            // ... and which chunk of that offset's source row
     uint32_t it0 = 0;       // pipeline slots consumed by earlier tiles (same sequence in every role)
     uint32_t tile_count = 0;                       // tiles with work so far (phase of nbr_bar)
     const bool bulk_nbr = (out_cap & 3) == 0;      // 16-byte aligned rows: cp.async.bulk can fetch them
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * kOsTileM;
-      const unsigned int mask = tile_mask[tile];
-      const int n_off = __popc(mask);
+      const unsigned int mask = os16_slot_mask(tile_mask[tile], pack);
+      const int n_off = __popc(mask);                 // slots' worth of offsets (groups of `pack`) present in the tile
       const int n_slots = n_off * n_kb;
 
       // stage nbr[k][row0 .. row0+127] for the active offsets (one global round trip per tile)
@@ -279,21 +319,28 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         for (int t = ptid; t > 0; --t) m &= m - 1;
         const int k = __ffs(m) - 1;
         if (ptid < n_off) koff_s[ptid] = k;
-        // neighbour rows of the tile by bulk copy (one 512-byte copy per active offset, no thread touches them)
-        const int rows = min(kOsTileM, out_cap - row0);
-        if (bulk_nbr && n_off > 0 && ptid == 0) mbar_arrive_expect_tx(nbr_bar, (uint32_t)(n_off * rows * 4));
         __syncwarp();
-        if (bulk_nbr && ptid < n_off)
-          tma_bulk_g2s(smem_u32(nbr_s + ptid * kOsTileM), nbr + (size_t)k * out_cap + row0, (uint32_t)(rows * 4), nbr_bar);
+        // neighbour rows of the tile by bulk copy (one 512-byte copy per offset of an active slot, no thread touches
+        // them): entry e = (slot e / pack, member e % pack) -> nbr_s[e][0..127]
+        const int rows = min(kOsTileM, out_cap - row0);
+        const int e_slot = ptid / pack;
+        const int k_src = ptid < n_off * pack ? koff_s[e_slot] * pack + (ptid - e_slot * pack) : k_vol;
+        const bool valid = k_src < k_vol;             // (the last group of a 27-offset kernel has phantom members)
+        const unsigned int vm = __ballot_sync(0xffffffffu, valid);
+        if (bulk_nbr && vm != 0u && ptid == 0) mbar_arrive_expect_tx(nbr_bar, (uint32_t)(__popc(vm) * rows * 4));
+        __syncwarp();
+        if (bulk_nbr && valid)
+          tma_bulk_g2s(smem_u32(nbr_s + ptid * kOsTileM), nbr + (size_t)k_src * out_cap + row0, (uint32_t)(rows * 4), nbr_bar);
       }
       if (bulk_nbr) {
         if (n_off > 0) D3B_WAIT(nbr_bar, tile_count & 1u, 5);
       } else {
         asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
 #pragma unroll 8
-        for (int idx = ptid; idx < n_off * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {   // independent loads
-          const int r = idx & 127;
-          nbr_s[idx] = __ldg(nbr + (size_t)koff_s[idx >> 7] * out_cap + min(row0 + r, out_cap - 1));
+        for (int idx = ptid; idx < n_off * pack * kOsTileM; idx += Cfg::kGroupThreads * Cfg::kGroups) {   // independent loads
+          const int r = idx & 127, e = idx >> 7;
+          const int k_src = koff_s[e / pack] * pack + e % pack;
+          nbr_s[idx] = k_src < k_vol ? __ldg(nbr + (size_t)k_src * out_cap + min(row0 + r, out_cap - 1)) : -1;
         }
       }
       asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroupThreads * Cfg::kGroups) : "memory");
@@ -302,7 +349,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
       for (int j = (int)((group + Cfg::kGroups - (it0 % Cfg::kGroups)) % Cfg::kGroups); j < n_slots; j += Cfg::kGroups) {
         const int n = j / n_kb, kb = j - n * n_kb;
-        const int ch = kb * kOsKc + c * 8;                 // this thread's 8 channels (16 bytes)
+        const int ch = pack > 1 ? c_src * 8 : kb * kOsKc + c * 8;     // this thread's 8 channels (16 bytes) of the source row
         const uint32_t it = it0 + (uint32_t)j;
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1u;
@@ -315,11 +362,11 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
           tma_bulk_g2s(stage + 2 * kOsABytes, packed + ((size_t)koff_s[n] * n_kb + kb) * (Cfg::kBBytes / 2), Cfg::kBBytes,
                        full_bar(s));
         }
-        if (ch < c_in_pad) {
+        if (pack > 1 || ch < c_in_pad) {
           // this thread: 16 consecutive rows (indices fetched as four 16-byte shared-memory loads), one 16-byte chunk
           const int row_base = wq * 64 + g * 16;
-          const int4* idx4 = reinterpret_cast<const int4*>(nbr_s + n * kOsTileM + row_base);
-          const bool col_live = ch < c_in;
+          const int4* idx4 = reinterpret_cast<const int4*>(nbr_s + (n * pack + sub) * kOsTileM + row_base);
+          const bool col_live = pack > 1 ? koff_s[n] * pack + sub < k_vol : ch < c_in;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const int4 iv = idx4[q4];
@@ -351,19 +398,28 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     constexpr uint32_t idesc1 = umma_idesc_f16(kOsTileM, COUT);       // A_lo x B_hi
     uint32_t it = 0, git = 0;          // slot counter (operand stages), group counter (accumulator buffers)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n_slots = __popc(tile_mask[tile]) * n_kb;
-      for (int j0 = 0; j0 < n_slots; j0 += Cfg::kFlush, ++git) {
+      const unsigned int smask = os16_slot_mask(tile_mask[tile], pack);
+      // accumulator groups are FIXED ranges of the full slot enumeration f = slot_offset * n_kb + kb (not runs of the
+      // slots that happen to be active in this tile): which partial sums share a truncating TMEM chain must not depend
+      // on the other rows of the tile
+      for (int f0 = 0; f0 < n_full; f0 += Cfg::kFlush) {
+        // (n_kb == 1 unless C_in > 64: no division on the usual path -- this warp's instruction stream is the critical one)
+        unsigned int members = 0u;                      // bit i: slot f0 + i is active in this tile
+        for (int i = 0; i < Cfg::kFlush && f0 + i < n_full; ++i)
+          members |= ((smask >> (n_kb == 1 ? f0 + i : (f0 + i) / n_kb)) & 1u) << i;
+        if (members == 0u) continue;
         const uint32_t buf = git & 1u;
         if (lane == 0) D3B_STAMP(4, git);
         D3B_WAIT(acc_empty(buf), ((git >> 1) & 1u) ^ 1u, 2);
         if (lane == 0) D3B_STAMP(5, git);
         const uint32_t d_addr = tmem_d + buf * Cfg::kBufCols;
-        const int j1 = min(j0 + Cfg::kFlush, n_slots);
-        for (int j = j0; j < j1; ++j, ++it) {
+        bool first = true;
+        for (int i = 0; i < Cfg::kFlush; ++i) {
+          if (!((members >> i) & 1u)) continue;
+          const int kb = n_kb == 1 ? 0 : (f0 + i) % n_kb;
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
-          const int kb = j % n_kb;
-          const int n_ks = min(kOsKc / 16, (c_in - kb * kOsKc + 15) / 16);
+          const int n_ks = min(kOsKc / 16, (c_eff - kb * kOsKc + 15) / 16);
           D3B_WAIT(full_bar(s), ph, 3);
           if (lane == 0) D3B_STAMP(6, it);
           tc_fence_after();
@@ -377,15 +433,18 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             for (int ks = 0; ks < kOsKc / 16; ++ks) {
               if (ks < n_ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);   // 16 f16 = 32 bytes along K = 2 descriptor address units
-                tc_mma_f16_if(issue, d_addr, da_hi + adv, db + adv, idesc2, (j > j0 || ks > 0) ? 1u : 0u);
+                tc_mma_f16_if(issue, d_addr, da_hi + adv, db + adv, idesc2, (!first || ks > 0) ? 1u : 0u);
                 tc_mma_f16_if(issue, d_addr, da_lo + adv, db + adv, idesc1, 1u);
               }
             }
             tc_commit_if(issue, empty_bar(s));      // frees the operand stage when these MMAs have read it
             if (lane == 0) D3B_STAMP(7, it);
           }
+          first = false;
+          ++it;
         }
         tc_commit_if(lane == 0 ? 1u : 0u, acc_full(buf));     // hands the group's partial sums to the accumulator warps
+        ++git;
       }
     }
   }
@@ -456,20 +515,23 @@ spconv_first16_kernel(const float* __restrict__ feat_in, const int* __restrict__
 }
 
 // ---- f16 weight image ------------------------------------------------------------------------------------------------
-// packed[k][kb][part][n][swizzled 64 halves], part 0 = hi, 1 = lo of w * 2^w_exp; zero beyond c_in.
+// packed[slot][kb][part][n][swizzled 64 halves], part 0 = hi, 1 = lo of w * 2^w_exp; zero beyond c_in.  slot = kernel
+// offset, or with offset packing (C_in 16 / 32, see os16_pack) a group of `pack` offsets side by side along K.
 __global__ void __launch_bounds__(256)
-pack_weight16_kernel(const float* __restrict__ w, int c_in, int c_out, int k_vol, int n_kb, float w_mul,
-                     __half* __restrict__ packed) {
-  const long long total = (long long)k_vol * n_kb * 2 * c_out * kOsKc;
+pack_weight16_kernel(const float* __restrict__ w, int c_in, int c_out, int k_vol, int n_slots_k, int n_kb, int pack,
+                     float w_mul, __half* __restrict__ packed) {
+  const long long total = (long long)n_slots_k * n_kb * 2 * c_out * kOsKc;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     long long t = e;
     const int cc = (int)(t % kOsKc); t /= kOsKc;
     const int n = (int)(t % c_out); t /= c_out;
     const int part = (int)(t % 2); t /= 2;
     const int kb = (int)(t % n_kb); t /= n_kb;
-    const int k = (int)t;
-    const int ci = kb * kOsKc + cc;
-    const float x = ci < c_in ? w[((size_t)k * c_in + ci) * c_out + n] * w_mul : 0.0f;
+    int k = (int)t;                                  // slot
+    int ci = kb * kOsKc + cc;
+    if (pack > 1) { k = k * pack + cc / c_in; ci = cc % c_in; }
+    const float x = (ci < c_in && k < k_vol) ? w[((size_t)k * c_in + ci) * c_out + n] * w_mul : 0.0f;
+    k = (int)t;
     __half hi, lo;
     split_f16(x, hi, lo);
     const size_t tile = (((size_t)k * n_kb + kb) * 2 + part) * (size_t)(c_out * kOsKc);
@@ -549,10 +611,12 @@ static int launch_os16(const d3b_conv16_params* p, const int32_t* nbr, const uin
   D3B_CUDA(ensure_dynamic_smem(spconv_os16_kernel<COUT>, Cfg::kSmemBytes, optin));
   const int n_tiles = div_up(out_cap, kOsTileM);
   const int grid = n_tiles < kNumSMs ? (n_tiles > 0 ? n_tiles : 1) : kNumSMs;
-  const int n_kb = (p->c_in + kOsKc - 1) / kOsKc;
+  const int pack = os16_pack(p->c_in, p->k_vol);
+  const int n_kb = pack > 1 ? 1 : (p->c_in + kOsKc - 1) / kOsKc;
   D3B_CUDA(launch_maybe_pdl(spconv_os16_kernel<COUT>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream,
                             (const __half*)p->in_hi, (const __half*)p->in_lo, (const int*)nbr, (const unsigned int*)tile_mask,
-                            (const int*)n_out, (int)out_cap, (int)p->c_in, n_kb, (const __half*)p->weight_packed, epi_of(p),
+                            (const int*)n_out, (int)out_cap, (int)p->c_in, n_kb, pack, (int)p->k_vol,
+                            (const __half*)p->weight_packed, epi_of(p),
                             (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32, (int*)p->overflow));
   D3B_LAUNCH_CHECK();
   return D3B_OK;
@@ -580,8 +644,9 @@ using namespace d3b;
 extern "C" size_t d3b_conv16_packed_weight_halves(int32_t c_in, int32_t c_out, int32_t k_vol) {
   if (c_in < 1 || c_in > 512 || k_vol < 1 || k_vol > 32) return 0;
   if (!(c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128)) return 0;
-  const int n_kb = (c_in + kOsKc - 1) / kOsKc;
-  return (size_t)k_vol * n_kb * 2 * c_out * kOsKc;
+  const int pack = os16_pack(c_in, k_vol);
+  const int n_kb = pack > 1 ? 1 : (c_in + kOsKc - 1) / kOsKc;
+  return (size_t)div_up(k_vol, pack) * n_kb * 2 * c_out * kOsKc;
 }
 
 extern "C" int d3b_conv16_pack_weight(const float* weight_dev, int32_t c_in, int32_t c_out, int32_t k_vol,
@@ -594,9 +659,10 @@ extern "C" int d3b_conv16_pack_weight(const float* weight_dev, int32_t c_in, int
     set_error("d3b_conv16_pack_weight: unsupported C_in=%d C_out=%d k_vol=%d", c_in, c_out, k_vol);
     return D3B_ERR_UNSUPPORTED;
   }
-  const int n_kb = (c_in + kOsKc - 1) / kOsKc;
-  pack_weight16_kernel<<<grid_for((long long)n, 256), 256, 0, stream>>>(weight_dev, c_in, c_out, k_vol, n_kb,
-                                                                        ldexpf(1.0f, w_exp), (__half*)packed_dev);
+  const int pack = os16_pack(c_in, k_vol);
+  const int n_kb = pack > 1 ? 1 : (c_in + kOsKc - 1) / kOsKc;
+  pack_weight16_kernel<<<grid_for((long long)n, 256), 256, 0, stream>>>(weight_dev, c_in, c_out, k_vol, div_up(k_vol, pack),
+                                                                        n_kb, pack, ldexpf(1.0f, w_exp), (__half*)packed_dev);
   D3B_LAUNCH_CHECK();
   return D3B_OK;
 }

@@ -19,6 +19,9 @@ METRICS = [
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_%"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_%"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_%"),
 ]
 
 

@@ -141,6 +141,21 @@ def test_host_api_and_batching(setup):
         assert torch.allclose(a["scores"], s["scores"], atol=1e-5)
 
 
+def test_detections_do_not_depend_on_batch_composition(setup):
+    """A cloud's detections are the same BITS whatever else shares its batch (sparse tiles straddle clouds: the
+    accumulation order of a row must not depend on its tile mates) -- what makes the sharded multi-GPU run
+    (tools/dist_infer.py --check) reproduce the single-rank result exactly."""
+    from det3d_b200.utils.synthetic import lidar_like_cloud
+    cfg, pipe, cpu = setup
+    c = [torch.from_numpy(lidar_like_cloud(9000 + 700 * i, cfg.voxel_generator.range, 4, 40 + i)).pin_memory() for i in range(4)]
+    alone = pipe.infer_host([c[0]]).clone()
+    ab = pipe.infer_host([c[0], c[1]]).clone()
+    cad = pipe.infer_host([c[2], c[0], c[3]]).clone()
+    assert int((alone[0, :, -1] > 0.5).sum()) > 0
+    assert torch.equal(alone[0], ab[0])
+    assert torch.equal(alone[0], cad[1])
+
+
 def test_model_predict_api(setup):
     """VoxelNet.forward(example, return_loss=False) with reference-style inputs (voxels [M,5,4])."""
     from det3d.core.input.voxel_generator import VoxelGenerator
