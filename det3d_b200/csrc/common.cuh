@@ -63,6 +63,11 @@ static inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, SmemO
   return e;
 }
 
+// nms.cu: `batch` box sets of one capacity in two launches (the detector's per-sample NMS); fmt_kernel 0 xyxyr (iou3d),
+// 1 xywlr (rotate_nms_cc), 2 axis-aligned, 3 axis-aligned "+1", 4 RRPN.
+int nms_batched(int fmt_kernel, const float* boxes, int n_cap, const int* n_dev, float thresh, int max_keep,
+                long long* keep_idx, int* keep_count, void* workspace, size_t workspace_bytes, int batch, cudaStream_t stream);
+
 // ---- programmatic dependent launch --------------------------------------------------------------------------------
 // The convolution kernels run back to back on one stream.  Launched with programmatic stream serialisation, kernel N+1 is
 // scheduled as soon as every CTA of kernel N has executed `griddepcontrol.launch_dependents` (they do so on entry): its

@@ -488,7 +488,11 @@ constexpr int kNmsPairQueue = 2048;     // queued (row, column) pairs of the iou
 template <int FMT>  // 0 xyxyr rotated, 1 xywlr rotated, 2 axis-aligned (xyxyr boxes, angle ignored), 3 axis-aligned "+1"
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restrict__ n_dev, float thresh,
-                int col_blocks, unsigned long long* __restrict__ mask) {
+                int col_blocks, unsigned long long* __restrict__ mask, long long box_stride, long long mask_stride) {
+  // blockIdx.y = box set of the batch (the detector runs one NMS per sample: all of them in one launch)
+  boxes += (size_t)blockIdx.y * box_stride;
+  mask += (size_t)blockIdx.y * mask_stride;
+  if (n_dev) n_dev += blockIdx.y;
   const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int nb = (n + kNmsBlock - 1) / kNmsBlock;
   const long long tri = (long long)nb * (nb + 1) / 2;
@@ -627,7 +631,12 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_cap, const int* __restric
 __global__ void __launch_bounds__(1024)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const int* __restrict__ n_dev,
                  int col_blocks_alloc, int max_keep, long long* __restrict__ keep_idx,
-                 int* __restrict__ keep_count, int stage_mask) {
+                 int* __restrict__ keep_count, int stage_mask, long long mask_stride) {
+  // blockIdx.x = box set of the batch
+  mask += (size_t)blockIdx.x * mask_stride;
+  keep_idx += (size_t)blockIdx.x * max_keep;
+  keep_count += blockIdx.x;
+  if (n_dev) n_dev += blockIdx.x;
   extern __shared__ unsigned long long remv[];
   __shared__ unsigned long long diag[kNmsBlock];
   __shared__ unsigned long long kept_word;
@@ -738,28 +747,33 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_cap, const i
   if (threadIdx.x == 0) *keep_count = kept_total;
 }
 
-static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* n_dev, float thresh,
-                      int max_keep, long long* keep_idx, int* keep_count, void* workspace,
-                      size_t workspace_bytes, cudaStream_t stream) {
+// `batch` independent box sets of the same capacity in two launches: set b has its boxes at boxes + b * n_cap * 5, its
+// live count at n_dev[b], its keep list at keep_idx + b * max_keep and keep_count[b]; the workspace holds one mask per set.
+int nms_batched(int fmt_kernel, const float* boxes, int n_cap, const int* n_dev, float thresh, int max_keep,
+                long long* keep_idx, int* keep_count, void* workspace, size_t workspace_bytes, int batch,
+                cudaStream_t stream) {
   const int col_blocks = div_up(n_cap, kNmsBlock);
-  const size_t need = (size_t)n_cap * col_blocks * 8;
+  const size_t per_set = d3b_nms_workspace_bytes(n_cap);
+  const size_t need = per_set * (size_t)batch;
   if (need > workspace_bytes) {
     set_error("nms: workspace %zu < %zu", workspace_bytes, need);
     return D3B_ERR_WORKSPACE;
   }
   unsigned long long* mask = (unsigned long long*)workspace;
+  const long long mask_stride = (long long)(per_set / 8), box_stride = (long long)n_cap * 5;
   const long long items = (long long)col_blocks * (col_blocks + 1) / 2 * kNmsSlices;
-  const int grid = (int)(items < (long long)kNumSMs * 16 ? (items > 0 ? items : 1) : (long long)kNumSMs * 16);
+  const int per_set_cap = kNumSMs * 16 / batch > 0 ? kNumSMs * 16 / batch : 1;
+  const dim3 grid((unsigned)(items < (long long)per_set_cap ? (items > 0 ? items : 1) : per_set_cap), (unsigned)batch);
   if (fmt_kernel == 0)
-    nms_mask_kernel<0><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<0><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask, box_stride, mask_stride);
   else if (fmt_kernel == 1)
-    nms_mask_kernel<1><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<1><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask, box_stride, mask_stride);
   else if (fmt_kernel == 2)
-    nms_mask_kernel<2><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<2><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask, box_stride, mask_stride);
   else if (fmt_kernel == 4)
-    nms_mask_kernel<4><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<4><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask, box_stride, mask_stride);
   else
-    nms_mask_kernel<3><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask);
+    nms_mask_kernel<3><<<grid, 256, 0, stream>>>(boxes, n_cap, n_dev, thresh, col_blocks, mask, box_stride, mask_stride);
   D3B_LAUNCH_CHECK();
   size_t smem = (size_t)col_blocks * 8;
   if (smem > 200 * 1024) {
@@ -771,10 +785,17 @@ static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* 
   if (stage_mask) smem = staged;
   static SmemOptIn sweep_optin;
   if (smem > 48 * 1024) D3B_CUDA(ensure_dynamic_smem(nms_sweep_kernel, 200 * 1024, sweep_optin));
-  nms_sweep_kernel<<<1, 1024, smem, stream>>>(mask, n_cap, n_dev, col_blocks, max_keep, keep_idx, keep_count,
-                                              stage_mask);
+  nms_sweep_kernel<<<batch, 1024, smem, stream>>>(mask, n_cap, n_dev, col_blocks, max_keep, keep_idx, keep_count,
+                                                  stage_mask, mask_stride);
   D3B_LAUNCH_CHECK();
   return D3B_OK;
+}
+
+static int nms_common(int fmt_kernel, const float* boxes, int n_cap, const int* n_dev, float thresh,
+                      int max_keep, long long* keep_idx, int* keep_count, void* workspace,
+                      size_t workspace_bytes, cudaStream_t stream) {
+  return nms_batched(fmt_kernel, boxes, n_cap, n_dev, thresh, max_keep, keep_idx, keep_count, workspace, workspace_bytes, 1,
+                     stream);
 }
 
 }  // namespace d3b

@@ -383,7 +383,7 @@ static PredictWs carve_predict(const d3b_predict_params* q, char* base) {
   w.n_valid = (int*)take(B * 4);
   w.keep_idx = (long long*)take(B * post * 8);
   w.keep_count = (int*)take(B * 4);
-  w.nms_ws_bytes = d3b_nms_workspace_bytes((int32_t)k);
+  w.nms_ws_bytes = d3b_nms_workspace_bytes((int32_t)k) * (size_t)q->batch;
   w.nms_ws = take(w.nms_ws_bytes);
   w.bytes = off;
   return w;
@@ -450,19 +450,11 @@ extern "C" int d3b_predict_task(const d3b_predict_params* q, float* packed, int3
   decode_selected_kernel<<<grid_for((long long)q->batch * q->pre_max, 256), 256, 0, stream>>>(
       p, w.sel_logit, w.sel_idx, w.cand, w.nms_boxes, w.scores, w.labels, w.dir_labels, w.n_valid);
   D3B_LAUNCH_CHECK();
-  for (int b = 0; b < q->batch; ++b) {
-    const float* boxes = w.nms_boxes + (size_t)b * q->pre_max * 5;
-    if (q->use_rotate_nms)
-      st = d3b_rotate_nms(boxes, q->pre_max, w.n_valid + b, D3B_BOX_XYWLR, q->nms_iou_threshold, q->post_max,
-                          (int64_t*)(w.keep_idx + (size_t)b * q->post_max), w.keep_count + b, w.nms_ws,
-                          w.nms_ws_bytes, stream);
-    else
-      st = d3b_normal_nms(boxes, q->pre_max, w.n_valid + b, D3B_AA_PIXEL /* box_torch_ops.nms, mg_head.py:1013-1017 */,
-                          q->nms_iou_threshold, q->post_max,
-                          (int64_t*)(w.keep_idx + (size_t)b * q->post_max), w.keep_count + b, w.nms_ws,
-                          w.nms_ws_bytes, stream);
-    if (st != D3B_OK) return st;
-  }
+  // one NMS per sample, all samples in the same two launches (mask, sweep)
+  st = nms_batched(q->use_rotate_nms ? 1 /* xywlr, rotate_nms_cc */ : 3 /* box_torch_ops.nms "+1", mg_head.py:1013-1017 */,
+                   w.nms_boxes, q->pre_max, w.n_valid, q->nms_iou_threshold, q->post_max, w.keep_idx, w.keep_count, w.nms_ws,
+                   w.nms_ws_bytes, q->batch, stream);
+  if (st != D3B_OK) return st;
   finalize_kernel<<<grid_for((long long)q->batch * q->post_max, 128), 128, 0, stream>>>(
       p, w.cand, w.scores, w.labels, w.dir_labels, w.keep_idx, w.keep_count, packed, packed_rows_per_sample,
       row_offset);
