@@ -24,6 +24,9 @@ from ..builder import build_loss
 from ..registry import HEADS
 
 
+_TASK_STREAMS = {}     # device -> side streams the per-task predict chains are forked over
+
+
 @HEADS.register_module
 class Head(nn.Module):
     def __init__(self, num_input, num_pred, num_cls, use_dir=False, num_dir=0, header=True, name="",
@@ -261,6 +264,7 @@ class MultiGroupHead(nn.Module):
         packed = bufs["packed"]
         rng = test_cfg["post_center_limit_range"]
         row_offset, flag = 0, 0
+        calls = []
         for task_id, preds in enumerate(preds_dicts):
             pre, post = posts[task_id]
             q = _lib.PredictParams()
@@ -294,12 +298,26 @@ class MultiGroupHead(nn.Module):
             ws = bufs["ws"].get(task_id)
             if ws is None or ws.numel() < need:
                 ws = bufs["ws"][task_id] = torch.empty(need, dtype=torch.uint8, device=dev)
-            with _lib.on_device_of(packed, first), _lib.timed("predict", anchors=int(anchors.shape[0]), batch=B, pre=pre, post=post):
-                st = _lib.lib().d3b_predict_task(C.byref(q), packed.data_ptr(), D, row_offset, None, ws.data_ptr(),
-                                                ws.numel(), _lib.current_stream())
-            _lib.check(st, "d3b_predict_task")
+            calls.append((q, ws, row_offset, dict(anchors=int(anchors.shape[0]), batch=B, pre=pre, post=post), anchors))
             row_offset += post
             flag += n_cls
+        # The tasks are independent (own head columns, own workspace, own rows of `packed`) and each is a chain of small
+        # launches: fork them over side streams so the chains overlap (CBGS: six tasks), join before anyone reads `packed`.
+        # Everything the calls read was enqueued before the fork; inside a CUDA-graph capture this becomes a fork/join.
+        main = torch.cuda.current_stream(dev)
+        pool = _TASK_STREAMS.setdefault(dev, [])      # (module-level: the head must stay deep-copyable)
+        while len(pool) < len(calls) - 1:
+            pool.append(torch.cuda.Stream(device=dev))
+        for side in pool[:len(calls) - 1]:
+            side.wait_stream(main)
+        for i, (q, ws, row0, info, _anchors) in enumerate(calls):
+            stream = main if i == 0 else pool[i - 1]
+            with torch.cuda.stream(stream), _lib.on_device_of(packed, first), _lib.timed("predict", **info):
+                st = _lib.lib().d3b_predict_task(C.byref(q), packed.data_ptr(), D, row0, None, ws.data_ptr(), ws.numel(),
+                                                _lib.current_stream())
+            _lib.check(st, "d3b_predict_task")
+        for side in pool[:len(calls) - 1]:
+            main.wait_stream(side)
         return _PackedDetections(packed, nd)
 
     def _predict_device_torch(self, example, preds_dicts, test_cfg):
