@@ -221,27 +221,35 @@ topk_finish_kernel(const unsigned long long* __restrict__ part, const int* __res
   // order: one broadcast shared-memory read per comparison, no barriers, and the candidates spread over the sample's
   // CTAs (a bitonic network over 8192 entries in one CTA cost 59 us here; 2048 entries 21 us).
   __syncthreads();
-  // T threads (consecutive lanes) share a candidate, each counting over 1/T of the list: the sample's threads are all busy
-  // whatever the list length (k + the rest of the pivot bin: 1.1k .. 8k entries)
-  const int total = n_cta * kTopkThreads;
-  int T = 1;
-  while (T < 32 && m * (T * 2) <= total) T <<= 1;
-  const int gid = cta * kTopkThreads + tid;
-  const int sub = gid & (T - 1);
-  const int chunk = ((m + T - 1) / T + 1) & ~1;                 // even, so the 16-byte reads stay aligned
-  const int j_lo = min(sub * chunk, m), j_hi = min(j_lo + chunk, m);
-  for (int base = 0; base < m; base += total / T) {            // warp-uniform trip count
-    const int c = base + gid / T;
+  // A group of 32 candidates (one per lane) is ranked by the whole CTA: warp w counts over the w-th 1/32 of the list, every
+  // lane of a warp reads the SAME entries (one broadcast wavefront per 16-byte read -- the loop is shared-memory-bandwidth
+  // bound: splitting the list over lanes instead cost 4 wavefronts per read and measured 56 us), the 32 partial ranks per
+  // candidate meet in shared memory.  Groups are dealt round-robin to the sample's CTAs.
+  __shared__ int s_rank[32];
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n_groups = (m + 31) / 32;
+  const int chunk = (((m + 31) / 32) + 1) & ~1;                  // even, so the 16-byte reads stay aligned
+  const int j_lo = min(warp * chunk, m), j_hi = min(j_lo + chunk, m);
+  for (int g = cta; g < n_groups; g += n_cta) {                 // CTA-uniform trip count
+    if (tid < 32) s_rank[tid] = 0;
+    __syncthreads();
+    const int c = g * 32 + lane;
     const unsigned long long x = c < m ? buf[c] : ~0ull;
     int rank = 0;
     int j = j_lo;
+#pragma unroll 4
     for (; j + 2 <= j_hi; j += 2) {
       const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(buf + j);
       rank += (y.x > x ? 1 : 0) + (y.y > x ? 1 : 0);
     }
     if (j < j_hi) rank += buf[j] > x ? 1 : 0;
-    for (int d = 1; d < T; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
-    if (sub == 0 && c < m && rank < k) emit(rank, x);
+    if (rank) atomicAdd(&s_rank[lane], rank);
+    __syncthreads();
+    if (warp == 0 && c < m) {
+      const int r = s_rank[lane];
+      if (r < k) emit(r, x);
+    }
+    __syncthreads();                                            // s_rank is reset by the next group
   }
   for (int j = m + cta * kTopkThreads + tid; j < k; j += n_cta * kTopkThreads) emit(j, 0ull);   // fewer candidates than k
 }
