@@ -121,6 +121,8 @@ SIGNATURES = {
     "d3b_abi_version": (C.c_int, []),
     "d3b_launch_count": (C.c_ulonglong, []),
     "d3b_set_pdl": (None, [C.c_int]),
+    "d3b_set_bev_variant": (None, [C.c_int]),
+    "d3b_get_bev_variant": (C.c_int, []),
     "d3b_voxelize_workspace_bytes": (_sz, [C.POINTER(VoxelCfg), _i32, _i32]),
     "d3b_voxelize": (C.c_int, [C.POINTER(VoxelCfg), _vp, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3b_ingest_workspace_bytes": (_sz, [_i32]),
@@ -228,8 +230,33 @@ def on_device_of(*tensors):
 PROFILE_EVENTS = None
 
 
+# bench.py hook, in-graph stage times: when set to a list and the current stream is being CAPTURED, `timed(tag)` records one
+# external timing event (an event-record node of the graph, cudaEventRecordExternal) whenever the stage tag changes on the
+# capture's origin stream -- a handful of nodes at stage boundaries, none between the launches of a stage (those keep their
+# programmatic edges).  After a replay, consecutive marks give each stage's duration inside the graph.
+GRAPH_MARKS = None
+
+
+def graph_mark(tag):
+    marks = GRAPH_MARKS
+    if marks is None:
+        return
+    import torch
+
+    if not torch.cuda.is_current_stream_capturing():
+        return
+    st = torch.cuda.current_stream()
+    if marks and (marks[0][2] != st.cuda_stream or marks[-1][0] == tag):
+        return          # a side stream of the capture (rulebook chain, forked task chains), or still the same stage
+    ev = torch.cuda.Event(enable_timing=True, external=True)
+    ev.record(st)
+    marks.append((tag, ev, st.cuda_stream))
+
+
 @contextlib.contextmanager
 def timed(tag, **info):
+    if GRAPH_MARKS is not None:
+        graph_mark(tag)
     events = PROFILE_EVENTS
     if events is None:
         yield

@@ -16,6 +16,7 @@ import warnings
 import numpy as np
 import torch
 
+from det3d_b200 import _lib
 from det3d_b200.core.anchor.anchor_generator import anchors_for_tasks
 from det3d_b200.models import build_detector
 from det3d_b200.ops.point_cloud.voxelize import Voxelizer
@@ -128,6 +129,7 @@ class InferencePipeline:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self.pack(self.forward_device(static_pts, list(key)))
+                _lib.graph_mark("end")          # (bench.py's in-graph stage timing; nothing unless _lib.GRAPH_MARKS is set)
             entry = self._graphs[key] = (graph, static_pts, out)
         graph, static_pts, out = entry
         static_pts.copy_(points, non_blocking=True)

@@ -355,6 +355,292 @@ bev_conv16_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   }
 }
 
+// ======================================================================================================================
+// Variant "channel-stationary" (3x3, stride 1, C_out = 128 per group, C_in % 64 == 0, up = 1): the GEMM is transposed,
+//     D^T[C_out = 128 (M, TMEM lanes), 256 pixels (N, TMEM columns)] += W[C_out, K16] . Act[256 pixels, K16]^T
+// so ONE N = 256 MMA covers the whole 16 x 16 pixel tile.  The kernel above runs the tile as two M = 128 halves: per
+// k-step six M128 x N128 MMAs re-read 48 KB of shared memory (A 4 KB + B 4 KB each) for 384 cycles of math, and the
+// shared-memory pipe (which also takes the TMA writes) caps the tensor pipe at ~45 % (ncu, clock-stamp traces).  Here
+// a k-step is three M128 x N256 MMAs: 36 KB of operand reads for the same 384 cycles, and half the instructions to issue
+// (one issuing thread suffices).  Same products, same order, same chain length (36) and truncation correction.
+//  * Activations: one TMA box per plane = 64 channels x 16 pixels x 18 rows: an image row is 2048 B (two swizzle groups),
+//    pixel (r, x) of the tile is operand row r * 16 + x, kernel row ky = descriptor start + ky * 2048.
+//  * Weights: the packed [W_hi | W_lo] image is K-major SW128 with C_out rows -- byte for byte usable as the A operand.
+//  * TMEM: 2 buffers x 256 columns; lane = output channel.  Eight accumulator warps: warp % 4 = lane quadrant (32
+//    channels), (warp - 2) / 4 = column half (128 pixels = 8 tile rows); a thread keeps 128 running sums of ONE channel,
+//    so bias / BN parameters are per-thread scalars.
+//  * Stores: the planes are NHWC, a thread holds one channel of 128 pixels.  Groups of 4 lanes transpose 4 pixels x 4
+//    channels of packed f16 with two warp shuffles per plane, then every lane writes 8 bytes (4 channels of one pixel):
+//    a warp store covers 4 pixels x 64 contiguous bytes.
+constexpr int kBwThreads = 352;                                   // warp 0 activation TMA, 1 MMA, 2..9 accumulators, 10 weights
+constexpr int kBwEpiWarp0 = 2;
+constexpr int kBwWeightWarp = 10;
+constexpr int kBwCout = 128;
+constexpr int kBwPatchRows = kBvTileY + 2;                        // 18
+constexpr int kBwRowBytes = kBvTileX * 128;                       // one image row of the patch: 16 pixels x 128 B
+constexpr int kBwPatchBytes = kBwPatchRows * kBwRowBytes;         // 36864
+constexpr int kBwAStageBytes = 2 * kBwPatchBytes;                 // hi, lo
+constexpr int kBwBBytes = 2 * kBwCout * 128;                      // [W_hi rows | W_lo rows]
+constexpr int kBwBStages = 2;
+constexpr int kBwAccCols = kBvTileY * kBvTileX;                   // 256 pixel columns per buffer
+constexpr int kBwTmemCols = 2 * kBwAccCols;                       // 512
+constexpr int kBwSmemBytes = kBvAStages * kBwAStageBytes + kBwBStages * kBwBBytes + 1024 + 256;
+static_assert(kBvAStages == 2, "the accumulator buffer index is the A stage index");
+
+__global__ void __launch_bounds__(kBwThreads, 1)
+bev_conv16_cs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, BvGeom g,
+                     const __half* __restrict__ packed, BvEpi epi, __half* __restrict__ out_hi,
+                     __half* __restrict__ out_lo, float* __restrict__ out_f32, int* __restrict__ overflow) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + kBvAStages * kBwAStageBytes;
+  const uint32_t bar_base = b_base + kBwBStages * kBwBBytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto acc_full = [&](uint32_t buf) { return bar_base + 8u * (8 + buf); };
+  auto acc_empty = [&](uint32_t buf) { return bar_base + 8u * (10 + buf); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * 12);
+
+  D3B_CTA_MARK(0);
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_group = g.batch * g.tiles_y * g.tiles_x;
+  const int n_tiles = tiles_per_group * g.groups;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1);
+      mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1);
+      mbar_init(acc_full(s), 1);       // tcgen05.commit after the 36 MMAs of one A stage
+      mbar_init(acc_empty(s), 256);    // all eight accumulator warps have read the buffer
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kBwTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  // (griddepcontrol.wait is executed by the threads that touch the previous layer's planes or write outputs: the activation
+  // producer and the accumulator warps; weight staging and the MMA issue run ahead of the previous grid's tail)
+
+  auto decode = [&](int tile, int& grp, int& b, int& y0, int& x0) {
+    grp = tile / tiles_per_group;
+    int t = tile - grp * tiles_per_group;
+    b = t / (g.tiles_y * g.tiles_x);
+    t -= b * g.tiles_y * g.tiles_x;
+    y0 = (t / g.tiles_x) * kBvTileY;
+    x0 = (t % g.tiles_x) * kBvTileX;
+  };
+
+  if (warp == 0) {
+    // ===================== activation producer (TMA tensor loads) =====================
+    // (Weights have their own producer warp: with one thread feeding both rings, the next patch load queued up behind a
+    // wait for a free weight stage and every A stage began with a ~2000-cycle bubble -- clock-stamp trace.)
+    if (lane == 0) {
+      pdl_wait_prior_grid();           // the planes are the previous layer's output
+      uint32_t a_it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int grp, b, y0, x0;
+        decode(tile, grp, b, y0, x0);
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          for (int kx = 0; kx < 3; ++kx, ++a_it) {
+            const int sa = a_it & 1;
+            D3B_STAMP(0, a_it);
+            D3B_WAIT(a_empty(sa), ((a_it >> 1) & 1u) ^ 1u, 1);
+            mbar_arrive_expect_tx(a_full(sa), kBwAStageBytes);
+            const uint32_t dst = a_base + sa * kBwAStageBytes;
+            tma_load_4d(dst, &tm_hi, kb * kBvKc, x0 + kx - g.pad, y0 - g.pad, b, a_full(sa));
+            tma_load_4d(dst + kBwPatchBytes, &tm_lo, kb * kBvKc, x0 + kx - g.pad, y0 - g.pad, b, a_full(sa));
+            D3B_STAMP(1, a_it);
+          }
+        }
+      }
+    }
+  } else if (warp == kBwWeightWarp) {
+    // ===================== weight producer (bulk copies; weights do not depend on the previous grid) =====================
+    if (lane == 0) {
+      uint32_t b_it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int grp = tile / tiles_per_group;
+        const __half* wgrp = packed + (size_t)grp * 9 * g.n_kb * (kBwBBytes / 2);
+        for (int kb = 0; kb < g.n_kb; ++kb) {
+          for (int kx = 0; kx < 3; ++kx) {
+            for (int ky = 0; ky < 3; ++ky, ++b_it) {
+              const int sb = b_it & 1;
+              D3B_STAMP(2, b_it);
+              D3B_WAIT(b_empty(sb), ((b_it >> 1) & 1u) ^ 1u, 2);
+              mbar_arrive_expect_tx(b_full(sb), kBwBBytes);
+              tma_bulk_g2s(b_base + sb * kBwBBytes, wgrp + ((size_t)(ky * 3 + kx) * g.n_kb + kb) * (kBwBBytes / 2),
+                           kBwBBytes, b_full(sb));
+              D3B_STAMP(3, b_it);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform stream, lane 0 issues) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(kBwCout, kBwAccCols);     // M = 128 channels, N = 256 pixels
+    const uint32_t issue = lane == 0 ? 1u : 0u;
+    uint32_t a_it = 0, b_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < g.n_kb; ++kb) {
+        for (int kx = 0; kx < 3; ++kx, ++a_it) {
+          const uint32_t sa = a_it & 1u;                                 // A stage == accumulator buffer
+          if (lane == 0) D3B_STAMP(4, a_it);
+          D3B_WAIT(acc_empty(sa), ((a_it >> 1) & 1u) ^ 1u, 3);
+          D3B_WAIT(a_full(sa), (a_it >> 1) & 1u, 4);
+          if (lane == 0) D3B_STAMP(5, a_it);
+          const uint32_t d_addr = tmem_d + sa * kBwAccCols;
+          for (int ky = 0; ky < 3; ++ky, ++b_it) {
+            const uint32_t sb = b_it & 1u;
+            D3B_WAIT(b_full(sb), (b_it >> 1) & 1u, 5);
+            if (lane == 0) D3B_STAMP(6, b_it);
+            tc_fence_after();
+            const uint32_t w_hi = b_base + sb * kBwBBytes;
+            const uint32_t x_hi = a_base + sa * kBwAStageBytes + (uint32_t)ky * kBwRowBytes;
+            const uint64_t dw_hi = umma_desc_sw128(w_hi), dw_lo = umma_desc_sw128(w_hi + kBwCout * 128);
+            const uint64_t dx_hi = umma_desc_sw128(x_hi), dx_lo = umma_desc_sw128(x_hi + kBwPatchBytes);
+#pragma unroll
+            for (int ks = 0; ks < kBvKc / 16; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              // small terms first, the dominant hi.hi product last (the order of the pixel-stationary kernel)
+              tc_mma_f16_if(issue, d_addr, dw_hi + adv, dx_lo + adv, idesc, (ky | ks) ? 1u : 0u);
+              tc_mma_f16_if(issue, d_addr, dw_lo + adv, dx_hi + adv, idesc, 1u);
+              tc_mma_f16_if(issue, d_addr, dw_hi + adv, dx_hi + adv, idesc, 1u);
+            }
+            tc_commit_if(issue, b_empty(sb));
+            if (lane == 0) D3B_STAMP(7, b_it);
+          }
+          tc_commit_if(issue, a_empty(sa));
+          tc_commit_if(issue, acc_full(sa));
+        }
+      }
+    }
+  } else {
+    // ===================== accumulator warps =====================
+    pdl_wait_prior_grid();                              // (output buffers may still be read by earlier kernels)
+    const int quad = warp & 3;                          // TMEM lane quadrant (warps 2..9: 2,3,0,1,2,3,0,1)
+    const int colhalf = (warp - kBwEpiWarp0) >> 2;      // pixels [128 * colhalf, +128) = tile rows [8 * colhalf, +8)
+    const int ch = quad * 32 + lane;                    // output channel of the group
+    const int n_groups = g.n_kb * 3;
+    const float f_fix = 1.f + 36.f * kTruncLossPerMma;  // 3 kernel rows x 4 k-steps x 3 products chained per buffer
+    bool ovf = false;
+    uint32_t a_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int grp, b, y0, x0;
+      decode(tile, grp, b, y0, x0);
+      float acc[128];
+#pragma unroll
+      for (int q = 0; q < 128; ++q) acc[q] = 0.f;
+#pragma unroll 1
+      for (int gi = 0; gi < n_groups; ++gi, ++a_it) {
+        const uint32_t buf = a_it & 1u;
+        if (warp == kBwEpiWarp0 && lane == 0) D3B_STAMP(8, a_it);
+        D3B_WAIT(acc_full(buf), (a_it >> 1) & 1u, 6);
+        if (warp == kBwEpiWarp0 && lane == 0) D3B_STAMP(9, a_it);
+        tc_fence_after();
+        const uint32_t t0 = tmem_d + buf * kBwAccCols + colhalf * 128 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r0[16], r1[16];
+          tc_ld16_nowait(t0 + c0, r0);
+          tc_ld16_nowait(t0 + c0 + 16, r1);
+          tc_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + q] = fmaf(__uint_as_float(r0[q]), f_fix, acc[c0 + q]);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[c0 + 16 + q] = fmaf(__uint_as_float(r1[q]), f_fix, acc[c0 + 16 + q]);
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));
+        if (warp == kBwEpiWarp0 && lane == 0) D3B_STAMP(10, a_it);
+      }
+      // ---- epilogue: per-channel scalars, 4 x 4 (pixel x channel) transposes through shuffles, 8-byte stores ----
+      const int cg = grp % g.cgroups;
+      const int pcol = grp * kBwCout + ch;
+      const float e_bias = epi.bias ? __ldg(epi.bias + pcol) : 0.f;
+      const float e_scale = epi.scale ? __ldg(epi.scale + pcol) : 1.f;
+      const float e_shift = epi.scale ? __ldg(epi.shift + pcol) : 0.f;
+      const size_t chan0 = (size_t)g.out_c0 + (size_t)cg * kBwCout;
+      const bool even = (lane & 1) == 0, low2 = (lane & 2) == 0;
+#pragma unroll
+      for (int q0 = 0; q0 < 128; q0 += 4) {
+        const int y = y0 + colhalf * 8 + (q0 >> 4);
+        const int xb = x0 + (q0 & 15);
+        uint32_t eh[4], el[4];                            // 16-bit patterns of the four pixels (this lane's channel)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = acc[q0 + j] * epi.acc_scale;
+          if (epi.bias) v += e_bias;
+          if (epi.scale) v = fmaf(v, e_scale, e_shift);
+          if (epi.relu) v = fmaxf(v, 0.f);
+          acc[q0 + j] = v;
+          __half h, l;
+          split_f16(v, h, l);
+          eh[j] = (uint32_t)__half_as_ushort(h);
+          el[j] = (uint32_t)__half_as_ushort(l);
+          ovf |= !(fabsf(v) < 65504.f);
+        }
+        if (out_f32 && y < g.h_out) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (xb + j < g.w_out)
+              out_f32[(((size_t)b * g.out_h + y) * g.out_w + xb + j) * (size_t)g.out_channels + chan0 + ch] = acc[q0 + j];
+        }
+        if (out_hi) {
+          // stage A (partner lane ^ 1): even lanes collect pixels 0 and 2, odd lanes pixels 1 and 3, for a channel pair
+          const uint32_t sh_h = even ? (eh[1] | (eh[3] << 16)) : (eh[0] | (eh[2] << 16));
+          const uint32_t sh_l = even ? (el[1] | (el[3] << 16)) : (el[0] | (el[2] << 16));
+          const uint32_t rh = __shfl_xor_sync(0xffffffffu, sh_h, 1), rl = __shfl_xor_sync(0xffffffffu, sh_l, 1);
+          uint32_t ua_h, ub_h, ua_l, ub_l;                // ua: pixel (lane & 1), ub: pixel 2 + (lane & 1); low half = lower channel
+          if (even) {
+            ua_h = eh[0] | (rh << 16);           ub_h = eh[2] | (rh & 0xffff0000u);
+            ua_l = el[0] | (rl << 16);           ub_l = el[2] | (rl & 0xffff0000u);
+          } else {
+            ua_h = (rh & 0xffffu) | (eh[1] << 16); ub_h = (rh >> 16) | (eh[3] << 16);
+            ua_l = (rl & 0xffffu) | (el[1] << 16); ub_l = (rl >> 16) | (el[3] << 16);
+          }
+          // stage B (partner lane ^ 2): lanes 0,1 of a quad keep pixels 0,1 and take the upper channel pair; lanes 2,3 keep 2,3
+          const uint32_t th = __shfl_xor_sync(0xffffffffu, low2 ? ub_h : ua_h, 2);
+          const uint32_t tl = __shfl_xor_sync(0xffffffffu, low2 ? ub_l : ua_l, 2);
+          const uint2 wh = low2 ? make_uint2(ua_h, th) : make_uint2(th, ub_h);
+          const uint2 wl = low2 ? make_uint2(ua_l, tl) : make_uint2(tl, ub_l);
+          const int x = xb + (lane & 3);
+          if (y < g.h_out && x < g.w_out) {
+            const size_t off = (((size_t)b * g.out_h + y) * g.out_w + x) * (size_t)g.out_channels + chan0 + quad * 32 + (lane & ~3);
+            *reinterpret_cast<uint2*>(out_hi + off) = wh;
+            *reinterpret_cast<uint2*>(out_lo + off) = wl;
+          }
+        }
+      }
+    }
+    if (warp == kBwEpiWarp0 && lane == 0) D3B_STAMP(11, 0);
+    if (ovf && overflow) atomicOr(overflow, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  D3B_CTA_MARK(1);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)kBwTmemCols)
+                 : "memory");
+  }
+}
+
 // ---- host side: tensor maps through the driver entry point (libcuda is not linked: CPU hosts must dlopen us) ----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -417,6 +703,26 @@ static int launch_bev(const d3b_bev16_params* p, const BvGeom& g, cudaStream_t s
   return D3B_OK;
 }
 
+// channel-stationary variant: 3x3, stride 1, one or more output blocks of exactly 128 channels, no sub-pixel groups
+static int launch_bev_cs(const d3b_bev16_params* p, const BvGeom& g, cudaStream_t stream) {
+  static SmemOptIn optin;
+  D3B_CUDA(ensure_dynamic_smem(bev_conv16_cs_kernel, kBwSmemBytes, optin));
+  CUtensorMap tm_hi, tm_lo;
+  int st = make_map(&tm_hi, p->in_hi, p->batch, p->h_in, p->w_in, p->c_in, kBvTileX, kBwPatchRows, 1);
+  if (st != D3B_OK) return st;
+  st = make_map(&tm_lo, p->in_lo, p->batch, p->h_in, p->w_in, p->c_in, kBvTileX, kBwPatchRows, 1);
+  if (st != D3B_OK) return st;
+  BvEpi e;
+  e.bias = p->bias; e.scale = p->scale; e.shift = p->shift; e.acc_scale = p->acc_scale; e.relu = p->relu;
+  const int n_tiles = g.batch * g.tiles_y * g.tiles_x * g.groups;
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  D3B_CUDA(launch_maybe_pdl(bev_conv16_cs_kernel, dim3(grid), dim3(kBwThreads), kBwSmemBytes, stream, tm_hi, tm_lo, g,
+                            (const __half*)p->weight_packed, e, (__half*)p->out_hi, (__half*)p->out_lo, p->out_f32,
+                            (int*)p->overflow));
+  D3B_LAUNCH_CHECK();
+  return D3B_OK;
+}
+
 }  // namespace d3b
 
 using namespace d3b;
@@ -450,6 +756,9 @@ extern "C" int d3b_bev_conv16(const d3b_bev16_params* p, void* stream_) {
   g.groups = p->groups; g.cgroups = p->cgroups; g.up = p->up;
   g.out_h = g.h_out * p->up; g.out_w = g.w_out * p->up;
   g.out_channels = p->out_channels; g.out_c0 = p->out_c0;
+  if (bev_variant() == 1 && p->ksize == 3 && p->stride == 1 && p->c_out == kBwCout && p->c_in % kBvKc == 0 && p->up == 1 &&
+      p->out_channels % 4 == 0)
+    return launch_bev_cs(p, g, stream);
 #define D3B_BEV_CASE(KS, ST)                                                   \
   if (p->ksize == KS && p->stride == ST) {                                     \
     switch (p->c_out) {                                                        \

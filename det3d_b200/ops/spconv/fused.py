@@ -220,6 +220,7 @@ class FusedSparseEncoder:
         # overlap is preserved as parallel branches when the forward is captured into a CUDA graph.
         main = torch.cuda.current_stream(device)
         ready = {}
+        planes_cleared = None
         builds = [(rb, build) for _L, rb, build in st["steps"] if build is not None]
         # the pair-based kernel accumulates with atomics into a zeroed buffer: one dedicated output buffer per layer,
         # so that all of a resolution's targets can be cleared up front, off the critical path
@@ -319,6 +320,15 @@ class FusedSparseEncoder:
         pool.append(t)
         return t
 
+    def _bev_planes(self, st, batch_size, device):
+        """NHWC f16 planes [B, H, W, C * D] of the encoder output (scn.py:192-195: dense.view(N, C * D, H, W))."""
+        planes = st.get("bev_planes")
+        if planes is None or planes.shape[0] != batch_size:
+            d, h, w = st["final_level"].spatial
+            c = self.plan[-1].conv.out_channels
+            planes = st["bev_planes"] = conv16.Planes((batch_size, h, w, c * d), device)
+        return planes
+
     def overflowed(self):
         """True if a feature left the f16 range since the last call (synchronises; the flag is then cleared).
         The caller must re-run with math='tf32x3' -- nothing was saturated silently."""
@@ -370,6 +380,11 @@ class FusedSparseEncoder:
                     ev = torch.cuda.Event()
                     ev.record(side)
                     ready[id(rb)] = ev
+                if bev_rows:
+                    # the BEV planes are cleared behind the rulebook chain, off the critical path (18 MB for SECOND)
+                    self._bev_planes(st, batch_size, device).zero_()
+                    planes_cleared = torch.cuda.Event()
+                    planes_cleared.record(side)
             builds = []
         waited = set()
 
@@ -394,10 +409,12 @@ class FusedSparseEncoder:
         d, h, w = final.spatial
         c = x.shape[-1]
         if bev_rows:
-            planes = st.get("bev_planes")
-            if planes is None:
-                planes = st["bev_planes"] = conv16.Planes((batch_size, h, w, c * d), device)
-            planes.zero_()
+            planes = self._bev_planes(st, batch_size, device)
+            assert tuple(planes.shape) == (batch_size, h, w, c * d)
+            if planes_cleared is not None:
+                main.wait_event(planes_cleared)
+            else:
+                planes.zero_()
             conv16.sparse_to_bev16(x, final, planes)
             if bev_rows == "planes":
                 return planes

@@ -39,6 +39,11 @@ unsigned long long d3b_launch_count(void);
 /* Programmatic dependent launch between consecutive convolution kernels of a stream (default on): the next kernel's
  * launch latency and prologue overlap the previous kernel's tail; results are unaffected. 0 = plain stream order. */
 void d3b_set_pdl(int on);
+/* Schedule of d3b_bev_conv16 for 3x3 stride-1 layers whose output blocks are 128 channels wide (the RPN blocks of
+ * necks/rpn.py:124-142): 1 = channel-stationary (one M128 x N256 MMA covers a 16 x 16 pixel tile, C_out on the TMEM
+ * lanes), 0 = pixel-stationary (two M128 x N128 halves).  Same products in the same order: results are bit-identical. */
+void d3b_set_bev_variant(int variant);
+int d3b_get_bev_variant(void);
 
 /* ========================================================================= *
  * 1. Voxelizer

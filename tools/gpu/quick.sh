@@ -1,8 +1,14 @@
 #!/bin/bash
+# scratch: in-graph stage times, both dense schedules
 mkdir -p gpurun_out
-timeout 300 python bench.py --dist uniform --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/bench_uniform.json 2>gpurun_out/bench_uniform.err; echo exit $?
+for v in 0 1; do
+D3B_BEV_VARIANT=$v timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-nms-c5 > gpurun_out/bench_v$v.json 2> gpurun_out/bench_v$v.err; echo "bench v$v exit $?"; tail -2 gpurun_out/bench_v$v.err
+done
 python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_uniform.json")); e=d["roofline_encoder"]
-print("uniform: value %.1f e2e %.1f ms %.3f | enc %.1f GB/s, %.3f ms, bytes %.1f MB, %.1f GFLOP" % (d["value"], d["e2e"]["value"], d["ms_per_step"], e["achieved"], e["kernel_ms_per_step"], e["algorithmic_bytes_per_step"]/1e6, e["flops_per_step"]/1e9))
+for v in (0, 1):
+    d=json.load(open("gpurun_out/bench_v%d.json" % v))
+    print("v%d: value %.1f e2e %.1f ms %.4f | roofline %.1f TF/s frac %.4f launch_ms %.4f" % (v, d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline"]["launch_ms"]))
+    print("   eager  ", {k: round(x,4) for k,x in d["stage_ms_per_step"].items()})
+    print("   graph  ", {k: round(x,4) for k,x in (d["stage_ms_per_step_in_graph"] or {}).items()})
 PY
