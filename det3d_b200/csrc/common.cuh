@@ -77,7 +77,7 @@ int nms_batched(int fmt_kernel, const float* boxes, int n_cap, const int* n_dev,
 // programmatic dependency.  d3b_set_pdl(0) turns it off (plain stream order).
 bool pdl_enabled();
 // bevconv16_sm100.cu: 0 = pixel-stationary tiles (two M128 halves) everywhere, 1 = channel-stationary N256 kernel for the
-// 3x3 stride-1 128-channel-block layers (d3b_set_bev_variant)
+// 3x3 stride-1 128-channel-block layers, 2 = channel-stationary when a CTA walks several tiles (d3b_set_bev_variant)
 int bev_variant();
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

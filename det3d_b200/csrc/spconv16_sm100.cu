@@ -88,6 +88,7 @@ struct OsEpi {
   const __half* res_lo;
   float acc_scale;
   int relu;
+  int seq;                        // launch counter of this translation unit (development traces only)
 };
 
 __device__ __forceinline__ bool epilogue16(float (&v)[16], const OsEpi& e, size_t row_off, int col, __half* out_hi,
@@ -192,7 +193,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
   int* koff_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 128);   // [32] active offsets
   int* nbr_s = reinterpret_cast<int*>(smem_gen + Cfg::kStages * Cfg::kStageBytes + 256);    // [32][128] neighbour rows
 
-  D3B_CTA_MARK(0);
+  D3B_CTA_MARK(0, epi.seq);
   pdl_launch_dependents();           // the next kernel of the stream may start its prologue behind this one's tail
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = min(*n_out_p, out_cap);
@@ -451,7 +452,7 @@ spconv_os16_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
   tc_fence_before();
   __syncthreads();
-  D3B_CTA_MARK(1);
+  D3B_CTA_MARK(1, epi.seq);
   if (warp == Cfg::kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
@@ -600,6 +601,8 @@ static OsEpi epi_of(const d3b_conv16_params* p) {
   e.bias = p->bias; e.scale = p->scale; e.shift = p->shift;
   e.res_hi = (const __half*)p->residual_hi; e.res_lo = (const __half*)p->residual_lo;
   e.acc_scale = p->acc_scale; e.relu = p->relu;
+  static std::atomic<int> launch_seq{0};
+  e.seq = launch_seq.fetch_add(1, std::memory_order_relaxed);
   return e;
 }
 
@@ -741,8 +744,8 @@ extern "C" int d3b_debug_fault_spconv16(unsigned int* host8) {
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(d3b::g_d3b_fault, zeros, 32);
   return (int)e;
 }
-extern "C" int d3b_debug_cta_ns_spconv16(unsigned long long* host512) {
-  return (int)cudaMemcpyFromSymbol(host512, d3b::g_d3b_cta_ns, sizeof(unsigned long long) * 512);
+extern "C" int d3b_debug_cta_ns_spconv16(unsigned long long* host4096) {
+  return (int)cudaMemcpyFromSymbol(host4096, d3b::g_d3b_cta_ns, sizeof(unsigned long long) * 4096);
 }
 extern "C" int d3b_debug_trace_spconv16(long long* host, int clear) {
   cudaError_t e = cudaMemcpyFromSymbol(host, d3b::g_d3b_trace, sizeof(long long) * 16 * 512);

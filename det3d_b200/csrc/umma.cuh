@@ -55,16 +55,17 @@ __device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, uns
 #define D3B_WAIT(bar, parity, code) mbar_wait_dbg(bar, parity, code)
 // clock-stamp trace of CTA 0 (development library only): g_d3b_trace[event][slot] = clock64()
 static __device__ long long g_d3b_trace[16 * 512];
-// per-CTA wall-clock span (ns, globaltimer): [2 * cta] = entry, [2 * cta + 1] = exit
-static __device__ unsigned long long g_d3b_cta_ns[2 * 256];
-__device__ __forceinline__ void d3b_cta_mark(int which) {
+// per-CTA wall-clock span (ns, globaltimer) of the last 8 launches: [(seq & 7) * 512 + 2 * cta] = entry, [.. + 1] = exit;
+// `seq` is a per-translation-unit launch counter passed by the host (baked into the node when a graph is captured)
+static __device__ unsigned long long g_d3b_cta_ns[8 * 2 * 256];
+__device__ __forceinline__ void d3b_cta_mark(int which, int seq) {
   if (threadIdx.x == 0 && blockIdx.x < 256) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_d3b_cta_ns[2 * blockIdx.x + which] = t;
+    g_d3b_cta_ns[(seq & 7) * 512 + 2 * blockIdx.x + which] = t;
   }
 }
-#define D3B_CTA_MARK(which) d3b_cta_mark(which)
+#define D3B_CTA_MARK(which, seq) d3b_cta_mark(which, seq)
 #define D3B_STAMP(ev, slot)                                                                        \
   do {                                                                                               \
     if (blockIdx.x == 0 && (unsigned)(slot) < 512u) g_d3b_trace[(ev) * 512 + (slot)] = clock64();  \
@@ -72,7 +73,7 @@ __device__ __forceinline__ void d3b_cta_mark(int which) {
 #else
 #define D3B_WAIT(bar, parity, code) mbar_wait(bar, parity)
 #define D3B_STAMP(ev, slot)
-#define D3B_CTA_MARK(which)
+#define D3B_CTA_MARK(which, seq)
 #endif
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

@@ -244,7 +244,8 @@ class BevConv16:
         p.overflow = _lib.ptr(overflow)
         with _lib.on_device_of(x.buf), _lib.timed(tag, flops=self.flops(b, h, w), c_in=self.c_in, c_out=self.c_out_total,
                                                   ksize=self.ksize, stride=self.stride, up=self.up, math="fp16x3",
-                                                  pixels_in=b * h * w, pixels_out=b * ho * wo):
+                                                  pixels_in=b * h * w, pixels_out=b * ho * wo,
+                                                  tiles=b * (-(-(ho // self.up) // 16)) * (-(-(wo // self.up) // 16)) * self.groups):
             st = _lib.lib().d3b_bev_conv16(C.byref(p), _lib.current_stream())
         _lib.check(st, "d3b_bev_conv16")
         return out if out is not None else out_f32

@@ -40,8 +40,9 @@ unsigned long long d3b_launch_count(void);
  * launch latency and prologue overlap the previous kernel's tail; results are unaffected. 0 = plain stream order. */
 void d3b_set_pdl(int on);
 /* Schedule of d3b_bev_conv16 for 3x3 stride-1 layers whose output blocks are 128 channels wide (the RPN blocks of
- * necks/rpn.py:124-142): 1 = channel-stationary (one M128 x N256 MMA covers a 16 x 16 pixel tile, C_out on the TMEM
- * lanes), 0 = pixel-stationary (two M128 x N128 halves).  Same products in the same order: results are bit-identical. */
+ * necks/rpn.py:124-142): 0 = pixel-stationary (two M128 x N128 halves per 16 x 16 pixel tile), 1 = channel-stationary
+ * (C_out on the TMEM lanes, one M128 x N256 MMA covers the tile), 2 = automatic (default: channel-stationary when the
+ * launch has at least two tiles per SM).  Same products in the same order: the results are bit-identical. */
 void d3b_set_bev_variant(int variant);
 int d3b_get_bev_variant(void);
 

@@ -15,9 +15,9 @@ def dump(tag, names, n_slots):
     for s in range(n_slots):
         print(s, " ".join("%7d" % (a[e, s] - t0 if a[e, s] > 0 else -1) for e in range(len(names))))
 def spans(tag, n_cta):
-    buf = (ctypes.c_ulonglong * 512)()
+    buf = (ctypes.c_ulonglong * 4096)()
     getattr(_lib.lib(), "d3b_debug_cta_ns_" + tag)(buf)
-    a = np.frombuffer(buf, dtype=np.uint64).reshape(256, 2)[:n_cta].astype(np.int64)
+    a = np.frombuffer(buf, dtype=np.uint64).reshape(8, 256, 2)[int(np.frombuffer(buf, dtype=np.uint64).reshape(8, 512).max(axis=1).argmax())][:n_cta].astype(np.int64)
     t0 = a[:, 0].min()
     dur = a[:, 1] - a[:, 0]
     print("== %s per-CTA spans (ns): start skew max %d, duration min/median/max %d/%d/%d, last end %d" % (
