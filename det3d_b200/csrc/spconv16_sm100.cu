@@ -747,6 +747,9 @@ extern "C" int d3b_debug_fault_spconv16(unsigned int* host8) {
 extern "C" int d3b_debug_cta_ns_spconv16(unsigned long long* host4096) {
   return (int)cudaMemcpyFromSymbol(host4096, d3b::g_d3b_cta_ns, sizeof(unsigned long long) * 4096);
 }
+extern "C" int d3b_debug_cta_clk_spconv16(long long* host4096) {
+  return (int)cudaMemcpyFromSymbol(host4096, d3b::g_d3b_cta_clk, sizeof(long long) * 4096);
+}
 extern "C" int d3b_debug_trace_spconv16(long long* host, int clear) {
   cudaError_t e = cudaMemcpyFromSymbol(host, d3b::g_d3b_trace, sizeof(long long) * 16 * 512);
   if (e == cudaSuccess && clear) {

@@ -58,11 +58,13 @@ static __device__ long long g_d3b_trace[16 * 512];
 // per-CTA wall-clock span (ns, globaltimer) of the last 8 launches: [(seq & 7) * 512 + 2 * cta] = entry, [.. + 1] = exit;
 // `seq` is a per-translation-unit launch counter passed by the host (baked into the node when a graph is captured)
 static __device__ unsigned long long g_d3b_cta_ns[8 * 2 * 256];
+static __device__ long long g_d3b_cta_clk[8 * 2 * 256];       // clock64() at the same two points: cycles / ns = the SM clock
 __device__ __forceinline__ void d3b_cta_mark(int which, int seq) {
   if (threadIdx.x == 0 && blockIdx.x < 256) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_d3b_cta_ns[(seq & 7) * 512 + 2 * blockIdx.x + which] = t;
+    g_d3b_cta_clk[(seq & 7) * 512 + 2 * blockIdx.x + which] = clock64();
   }
 }
 #define D3B_CTA_MARK(which, seq) d3b_cta_mark(which, seq)

@@ -12,13 +12,17 @@ def report(tag, n_cta, n_launch, t_graph_us):
     buf = (ctypes.c_ulonglong * 4096)()
     getattr(_lib.lib(), "d3b_debug_cta_ns_" + tag)(buf)
     a = np.frombuffer(buf, dtype=np.uint64).reshape(8, 256, 2)[:, :n_cta].astype(np.int64)
+    cb = (ctypes.c_longlong * 4096)()
+    getattr(_lib.lib(), "d3b_debug_cta_clk_" + tag)(cb)
+    c = np.frombuffer(cb, dtype=np.int64).reshape(8, 256, 2)[:, :n_cta]
     order = np.argsort(a[:, :, 0].min(axis=1))[-n_launch:]
     t0 = a[order[0], :, 0].min()
     prev_end = None
     for s in order:
         st, en = a[s, :, 0] - t0, a[s, :, 1] - t0
-        print("   launch slot %d: first start %6d  last start %6d  first end %6d  last end %6d  median span %5d ns%s" % (
-            s, st.min(), st.max(), en.min(), en.max(), int(np.median(en - st)),
+        ghz = np.median((c[s, :, 1] - c[s, :, 0]) / np.maximum(a[s, :, 1] - a[s, :, 0], 1))
+        print("   launch slot %d: first start %6d  last start %6d  first end %6d  last end %6d  median span %5d ns = %6d cycles (SM clock %.2f GHz)%s" % (
+            s, st.min(), st.max(), en.min(), en.max(), int(np.median(en - st)), int(np.median(c[s, :, 1] - c[s, :, 0])), ghz,
             "" if prev_end is None else "   gap after previous launch's last end: %d ns" % (st.min() - prev_end)))
         prev_end = en.max()
     print("   graph replay (events): %.1f us total, %.1f us per launch" % (t_graph_us, t_graph_us / n_launch), flush=True)
@@ -46,7 +50,16 @@ layers = [conv16.BevConv16(torch.randn(9, 128, 128, device=dev) * 0.03, 3, pad=1
 def dense_chain():
     for i, L in enumerate(layers):
         L(P[i % 2], out=P[(i + 1) % 2])
-for pdl in (1, 0):
+import time
+def isolated(variant):
+    _lib.lib().d3b_set_bev_variant(variant)
+    for _ in range(3):
+        layers[0](P[0], out=P[1]); torch.cuda.synchronize(); time.sleep(0.02)
+    print("== dense, variant %d, ISOLATED launch (20 ms idle before it)" % variant)
+    report("bevconv16", 143, 1, 0.0)
+for variant in (0, 1):
+    isolated(variant)
+for pdl in (0, 1):
     _lib.lib().d3b_set_pdl(pdl)
     for variant in (0, 1):
         _lib.lib().d3b_set_bev_variant(variant)
@@ -60,7 +73,7 @@ cws = [conv16.ConvWeights16(torch.randn(27, 64, 64, device=dev) * 0.05, relu=Tru
 def sparse_chain():
     for i, cw in enumerate(cws):
         conv16.sparse_conv16(X[i % 2], rb, cw, X[(i + 1) % 2])
-for pdl in (1, 0):
+for pdl in (0,):
     _lib.lib().d3b_set_pdl(pdl)
     print("== sparse chain (13000 rows = 102 tiles, 64->64), pdl %d" % pdl)
     run_graph(sparse_chain, 6, "spconv16", 102)
