@@ -26,7 +26,7 @@ def main():
         out.append("| %s | %s | %.1f | %.3f | %.1f | %d | %s MHz |" % (
             d["config"].get("baseline_config", "?"), d["config"]["workload"], d["value"], d["ms_per_step"], d["e2e"]["value"],
             round(d["gpu_launches"] / d["steps"]), d["clocks"].get("sm_mhz")))
-    out += ["", "## Rooflines (per-stage pass of the same run: CUDA events around every C-ABI call on its launching stream)", ""]
+    out += ["", "## Rooflines (dense 3x3 and encoder: durations inside the replayed graph; the others: CUDA events around every C-ABI call of an eager pass)", ""]
     out += ["| config | kernel | bound | achieved | peak | frac | share of step |", "|---|---|---|---|---|---|---|"]
     for d in rows:
         for key in ("roofline", "roofline_encoder", "roofline_rulebook", "roofline_voxelize", "roofline_nms"):
@@ -39,6 +39,16 @@ def main():
             share = "%.3f" % r["share_of_step"] if "share_of_step" in r else "-"
             out.append("| %s | %s | %s | %s | %s | %s | %s |" % (d["config"].get("baseline_config", "?"), r["kernel"][:90],
                                                                r["bound"], ach, peak, frac, share))
+    if any(d.get("stage_ms_per_step_in_graph") for d in rows):
+        out += ["", "## Stage times inside the replayed CUDA graph (external timing events at the stage boundaries) vs the eager per-call pass", "",
+                "| config | stage | in graph [ms/step] | eager pass [ms/step] (adds the host cost of every call) |", "|---|---|---|---|"]
+        for d in rows:
+            g = d.get("stage_ms_per_step_in_graph") or {}
+            e = d.get("stage_ms_per_step") or {}
+            for k in g:
+                out.append("| %s | %s | %.4f | %s |" % (d["config"].get("baseline_config", "?"), k, g[k], "%.4f" % e[k] if k in e else "-"))
+            if g:
+                out.append("| %s | **sum** | %.4f | (step: %.4f) |" % (d["config"].get("baseline_config", "?"), sum(g.values()), d["ms_per_step"]))
     out += ["", "## CPU baseline (reference path on the host cores of the same box)", ""]
     out += ["| config | port clouds/s (cores) | reference voxelizer, 1 thread: full call / loop only | pool of host cores |", "|---|---|---|---|"]
     for d in rows:
