@@ -516,7 +516,8 @@ def main():
     #      durations the stages have INSIDE the product graph -- the eager pass above adds the host-side cost of every call
     #      (ctypes, two tensor-map encodes per dense layer, launch latency) between its events. ----
     graph_ms = {}
-    if use_graph:
+    if use_graph and world == 1:       # (N > 1: a second capture next to a live NCCL communicator is not worth the risk;
+        #                                 the N = 1 line carries the rooflines)
         pipe._graphs.clear()
         _lib.GRAPH_MARKS = marks = []
         try:
