@@ -119,3 +119,17 @@ def test_rrpn_oracle_matches_reference_golden():
             assert np.array_equal(keep, want)
         else:
             assert len(set(keep.tolist()) ^ set(want.tolist())) <= 2 * near
+
+
+def test_oracle_anchor_decode_pinned_to_reference_golden():
+    """oracle/predict_cpu.second_box_decode (the decode of the CPU predict restatement) against the reference function
+    executed through the reference coder's call (tests/golden/make_golden_decode.py, box_torch_ops.py:79-148)."""
+    import os
+    import torch
+    from oracle.predict_cpu import second_box_decode
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode_coder.npz"))
+    for nd in (7, 9):
+        for vec in (False, True):
+            key = "nd%d_vec%d_lin0" % (nd, int(vec))
+            got = second_box_decode(torch.from_numpy(g[key + "_enc"]), torch.from_numpy(g[key + "_anchors"]), vec).numpy()
+            assert np.allclose(got, g[key + "_out"], rtol=0, atol=1e-6), key

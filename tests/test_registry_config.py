@@ -132,3 +132,26 @@ def test_bn_fold_and_plan():
     assert len(p) == 14 and all(L.bn is not None and L.relu for L in p)
     p = compile_plan(SpMiddleResNetFHD(num_input_features=5).middle_conv)
     assert len(p) == 21 and sum(L.residual for L in p) == 8 and sum(L.save_identity for L in p) == 8
+
+
+def test_box_coder_decode_matches_reference_golden_including_its_quirk():
+    """GroundBox3dCoderTorch.decode_torch against the reference function run through the reference coder's own call
+    (tests/golden/make_golden_decode.py): `linear_dim` lands in the ignored `bin_loss` slot and `norm_velo` is never
+    forwarded (box_coders.py:106-109), so sizes always decode with exp() and velocities without the diagonal -- whatever the
+    coder was built with.  The device predict path sets smooth_dim = norm_velo = 0 for the same reason (mg_head.py)."""
+    import os
+    import numpy as np
+    import torch
+    from det3d_b200.core.bbox.box_coders import GroundBox3dCoderTorch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode_coder.npz"))
+    for nd in (7, 9):
+        for vec in (False, True):
+            for lin in (False, True):
+                key = "nd%d_vec%d_lin%d" % (nd, int(vec), int(lin))
+                coder = GroundBox3dCoderTorch(linear_dim=lin, vec_encode=vec, n_dim=nd, norm_velo=True)
+                assert coder.code_size == nd + (1 if vec else 0)
+                got = coder.decode_torch(torch.from_numpy(g[key + "_enc"]), torch.from_numpy(g[key + "_anchors"])).numpy()
+                assert got.shape == g[key + "_out"].shape
+                assert np.allclose(got, g[key + "_out"], rtol=0, atol=1e-6), key
+            # the flag changes nothing in the reference either
+            assert np.array_equal(g["nd%d_vec%d_lin0_out" % (nd, int(vec))][:, 3:6] > 0, np.ones((257, 3), bool))
